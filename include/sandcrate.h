@@ -1,0 +1,135 @@
+/*
+ * sandcrate.h - C ABI of the B200 (sm_100a) implementation of SandCrate's per-timestep particle step.
+ *
+ * The reference (David-Taub/sand_crate) has no FFI: its step is the Python method `Crate.physics_tick()`
+ * (src/crate/crate.py:91-129).  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md; the in-repo binding is sand_crate_b200/_lib.py).  Each entry point cites the reference
+ * code it replaces.  Plain pointers and sizes only; every `const double*` / `double*` is a HOST pointer borrowed
+ * for the duration of the call unless the name says `_dev`.
+ *
+ * Conventions
+ *   - return value: 0 = ok, non-zero = error; `sc_last_error(ctx)` (or `sc_last_error(NULL)` for `sc_create`)
+ *     returns the message.  CUDA errors are reported, never swallowed; there is no CPU fallback.
+ *   - one context per GPU, not thread-safe, all work on one CUDA stream.
+ *   - particles keep their identity (a stable 32-bit uid = order of insertion); every host-visible per-particle
+ *     array is in the reference's "original index" order (ascending uid among live particles), exactly like
+ *     the rows of `Crate.particles` (crate.py:24, 146-159).
+ */
+#ifndef SANDCRATE_H
+#define SANDCRATE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_MAX_NEIGHBORS 20 /* collision_detector.py:6 MAX_ALLOWED_NEIGHBORS */
+#define SC_MAX_SEGMENTS 32  /* wall segments per scene (stirring_cup: 6, wave_machine: 8) */
+#define SC_MAX_BODIES 16
+
+typedef struct sc_ctx sc_ctx;
+
+/* world.coefficients of config/*.yaml (stirring_cup.yaml:9-22), the ones the step reads (crate.py:42-57).
+ * spring_overlap_balance / spring_amplifier are dead in the reference (crate.py:117-118) and max_particles is a
+ * host-side source limit, so they are not part of the device parameter block. */
+typedef struct sc_params {
+    double dt;
+    double particle_radius;
+    double wall_collision_decay;
+    double pressure_amplifier;
+    double ignored_pressure;
+    double collider_noise_level;
+    double viscosity;
+    double surface_smoothing;
+    double target_pressure;
+    double gravity_x;
+    double gravity_y;
+} sc_params;
+
+/* arithmetic mode of the pair / force kernels */
+#define SC_PRECISION_F64 0   /* fp64, no FMA contraction, reference summation orders: bit-exact parity mode */
+#define SC_PRECISION_MIXED 1 /* positions fp64 in HBM, pair differences fp64 -> fp32, forces/velocities fp32 */
+
+/* source of the per-directed-pair collider noise (crate.py:168-170) */
+#define SC_NOISE_NONE 0    /* term skipped; exact when collider_noise_level == 0 */
+#define SC_NOISE_COUNTER 1 /* counter-based: mix64((uid_i << 32 | uid_j) ^ tick_key(seed, tick)) */
+#define SC_NOISE_HOST 2    /* the caller supplies the reference's own np.random.rand stream per tick */
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+/* `stream` is a cudaStream_t the caller owns (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a
+ * private stream.  `capacity` = maximum number of live particles (crate.py `max_particles`). */
+int sc_create(int device, int precision, int64_t capacity, void *stream, sc_ctx **out);
+void sc_destroy(sc_ctx *ctx);
+const char *sc_last_error(const sc_ctx *ctx);
+int sc_version(void);
+
+/* ---- configuration (re-read every tick by the reference: playback.py:221-226 edits coefficients live) --- */
+int sc_set_params(sc_ctx *ctx, const sc_params *p);                 /* crate.py:55-57 */
+/* segments: S x 4 (ax, ay, bx, by) = `Crate.segments` (crate.py:69-71) AFTER apply_bodies_velocity
+ * (crate.py:363-365); body_len[nbodies] = segments per body; body_kin: nbodies x 5 =
+ * (center_velocity.x, .y, angular_clockwise_velocity, position.x, .y) (rigid_body.py:18-34). */
+int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const int32_t *body_len, const double *body_kin,
+                 int nbodies);
+int sc_set_noise(sc_ctx *ctx, int mode, uint64_t seed);
+int sc_set_tick(sc_ctx *ctx, uint64_t tick);                        /* crate.py:23, 127 */
+
+/* ---- state ------------------------------------------------------------------------------------------- */
+int sc_set_state(sc_ctx *ctx, const double *pos, const double *vel, int64_t n); /* uid = 0..n-1 */
+/* create_new_particles (crate.py:138-147): appended rows get the next uids. */
+int sc_append_particles(sc_ctx *ctx, const double *pos, const double *vel, int64_t n);
+int sc_particle_count(sc_ctx *ctx, int64_t *n);                     /* crate.py:87-89; synchronises */
+/* any of pos / vel / pressure may be NULL.  pos, vel: n x 2; pressure: n (crate.py:26, 275). */
+int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *pressure, int64_t cap, int64_t *n);
+int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n);
+
+/* ---- the step ------------------------------------------------------------------------------------------ */
+/* One tick = remove_particles (crate.py:149-159) -> calc_virtual_colliders + apply_hard_wall_fix (213-243,
+ * 202-211) -> detect_particle_collisions (collision_detector.py:9-49) -> populate_colliders (161-175) ->
+ * pressures (261-284) -> tension, gravity, pressure, viscosity (335-353, 309-310, 295-307, 316-323) ->
+ * wall bounce (245-259) -> continuous collision (177-200) -> integration (360-361); tick += 1.
+ * Asynchronous: returns after enqueueing.  Not valid with SC_NOISE_HOST (use begin/finish). */
+int sc_step(sc_ctx *ctx);
+int sc_step_n(sc_ctx *ctx, int nsteps);
+/* Split form for SC_NOISE_HOST: `begin` runs everything up to and including the neighbor search and returns
+ * the live particle count and the number of directed pairs sum(K_i); the caller draws `n_pairs x 2` uniforms
+ * from the reference's generator (CSR order: particle ascending, slot ascending, x then y - crate.py:165-170)
+ * and passes them to `finish`.  With other noise modes `noise` is ignored. */
+int sc_step_begin(sc_ctx *ctx, int64_t *n_particles, int64_t *n_pairs);
+int sc_step_finish(sc_ctx *ctx, const double *noise);
+int sc_synchronize(sc_ctx *ctx);
+
+/* ---- parity taps (valid after sc_step / sc_step_begin; all in original index order) -------------------- */
+/* pos_search: positions the search ran on (after apply_hard_wall_fix); rows_sorted / order:
+ * `y_floored[sorted_indices]`, `sorted_indices` of strip_sort_particles (collision_detector.py:124-128). */
+int sc_get_search(sc_ctx *ctx, double *pos_search, int64_t *rows_sorted, int64_t *order, int64_t cap);
+/* `colliders_indices` (crate.py:102): counts[n], idx[n x 20] holding original indices, -1 padded. */
+int sc_get_neighbors(sc_ctx *ctx, int32_t *counts, int32_t *idx, int64_t cap);
+/* surface normals of apply_tension pass 1 (crate.py:337-342), n x 2. */
+int sc_get_tension(sc_ctx *ctx, double *tension, int64_t cap);
+/* number of wall contacts V_i per particle (crate.py:229-232) of the last tick. */
+int sc_get_wall_counts(sc_ctx *ctx, int32_t *counts, int64_t cap);
+
+/* ---- the reference's layer-2 functions as standalone device ops ---------------------------------------- */
+/* detect_particle_collisions(particles, diameter) (collision_detector.py:9-49) on arbitrary coordinates. */
+int sc_detect_particle_collisions(sc_ctx *ctx, const double *particles, int64_t P, double diameter,
+                                  int64_t *rows_sorted, int64_t *order, int32_t *counts, int32_t *idx);
+/* points_to_segments_distance (geometry_utils.py:7-39): nearest P x S x 2, dist P x S. */
+int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int64_t P, const double *segments, int S,
+                                   double *nearest, double *dist);
+/* pad_segments (geometry_utils.py:146-172): padded 2S x 4. */
+int sc_pad_segments(const double *segments, int S, double pad, double *padded);
+
+/* ---- measurement ---------------------------------------------------------------------------------------- */
+/* Per-kernel CUDA-event timing on the context's stream.  sc_profile_read returns, for each kernel slot, the
+ * number of launches and the summed milliseconds since sc_profile_enable(ctx, 1). */
+#define SC_PROFILE_SLOTS 16
+int sc_profile_enable(sc_ctx *ctx, int on);
+int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int slots);
+const char *sc_profile_name(int slot);
+int64_t sc_launch_count(const sc_ctx *ctx); /* kernels launched by this context so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SANDCRATE_H */

@@ -19,6 +19,7 @@ What is recorded:
 from __future__ import annotations
 
 import argparse
+import json
 import os
 import sys
 import time
@@ -68,7 +69,9 @@ def record_config(ref, name, quick):
             free[f"pressure_t{tick}"] = np.asarray(rc.crate.particles_pressure, dtype=np.float64).copy()
         if tick % 50 == 0:
             print(f"  {name}: tick {tick}/{last}  P={rc.crate.particle_count}  {time.time() - t0:.0f}s", flush=True)
-    save(f"freerun_{name}.npz", ticks=np.array(free_ticks), **free)
+    world = {"coefficients": cfg.world_config.coefficients, "particle_sources": cfg.world_config.particle_sources,
+             "rigid_bodies": cfg.world_config.rigid_bodies}
+    save(f"freerun_{name}.npz", ticks=np.array(free_ticks), world_json=np.array(json.dumps(world)), **free)
 
 
 def neighbor_cases(ref):

@@ -1,0 +1,278 @@
+"""ctypes binding of include/sandcrate.h (libsandcrate.so, sm_100a).
+
+This is the only way the Python host side reaches the GPU: there is no CPU fallback.  If the shared library is
+missing it is built in-tree with nvcc (sand_crate_b200/build.py); if that fails, or no B200 is visible when a
+context is created, the call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MAX_NEIGHBORS = 20
+MAX_SEGMENTS = 32
+MAX_BODIES = 16
+PROFILE_SLOTS = 16
+
+PRECISION_F64 = 0
+PRECISION_MIXED = 1
+NOISE_NONE = 0
+NOISE_COUNTER = 1
+NOISE_HOST = 2
+
+PARAM_FIELDS = ("dt", "particle_radius", "wall_collision_decay", "pressure_amplifier", "ignored_pressure",
+                "collider_noise_level", "viscosity", "surface_smoothing", "target_pressure", "gravity_x", "gravity_y")
+
+
+class ScParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in PARAM_FIELDS]
+
+
+class SandCrateError(RuntimeError):
+    pass
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+_up = C.POINTER(C.c_uint32)
+_ctx = C.c_void_p
+
+# name -> (restype, argtypes); tests/test_abi.py checks that every function declared in include/sandcrate.h is here
+SIGNATURES = {
+    "sc_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(_ctx)]),
+    "sc_destroy": (None, [_ctx]),
+    "sc_last_error": (C.c_char_p, [_ctx]),
+    "sc_version": (C.c_int, []),
+    "sc_set_params": (C.c_int, [_ctx, C.POINTER(ScParams)]),
+    "sc_set_walls": (C.c_int, [_ctx, _dp, C.c_int, _ip, _dp, C.c_int]),
+    "sc_set_noise": (C.c_int, [_ctx, C.c_int, C.c_uint64]),
+    "sc_set_tick": (C.c_int, [_ctx, C.c_uint64]),
+    "sc_set_state": (C.c_int, [_ctx, _dp, _dp, C.c_int64]),
+    "sc_append_particles": (C.c_int, [_ctx, _dp, _dp, C.c_int64]),
+    "sc_particle_count": (C.c_int, [_ctx, _lp]),
+    "sc_get_state": (C.c_int, [_ctx, _dp, _dp, _dp, C.c_int64, _lp]),
+    "sc_get_uids": (C.c_int, [_ctx, _up, C.c_int64, _lp]),
+    "sc_step": (C.c_int, [_ctx]),
+    "sc_step_n": (C.c_int, [_ctx, C.c_int]),
+    "sc_step_begin": (C.c_int, [_ctx, _lp, _lp]),
+    "sc_step_finish": (C.c_int, [_ctx, _dp]),
+    "sc_synchronize": (C.c_int, [_ctx]),
+    "sc_get_search": (C.c_int, [_ctx, _dp, _lp, _lp, C.c_int64]),
+    "sc_get_neighbors": (C.c_int, [_ctx, _ip, _ip, C.c_int64]),
+    "sc_get_tension": (C.c_int, [_ctx, _dp, C.c_int64]),
+    "sc_get_wall_counts": (C.c_int, [_ctx, _ip, C.c_int64]),
+    "sc_detect_particle_collisions": (C.c_int, [_ctx, _dp, C.c_int64, C.c_double, _lp, _lp, _ip, _ip]),
+    "sc_points_to_segments_distance": (C.c_int, [_ctx, _dp, C.c_int64, _dp, C.c_int, _dp, _dp]),
+    "sc_pad_segments": (C.c_int, [_dp, C.c_int, C.c_double, _dp]),
+    "sc_profile_enable": (C.c_int, [_ctx, C.c_int]),
+    "sc_profile_read": (C.c_int, [_ctx, _lp, _dp, C.c_int]),
+    "sc_profile_name": (C.c_char_p, [C.c_int]),
+    "sc_launch_count": (C.c_int64, [_ctx]),
+}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """dlopen libsandcrate.so (building it first if the sources are newer).  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise SandCrateError(f"{_build.LIB} is missing and could not be built; there is no CPU fallback")
+    L = C.CDLL(_build.LIB)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _f64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape_last is not None:
+        a = a.reshape(-1, shape_last)
+    return a
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+class Context:
+    """Owns one `sc_ctx`.  Thin: every method is one C-ABI call plus NumPy buffer management."""
+
+    def __init__(self, capacity: int, precision: int = PRECISION_F64, device: int = 0, stream: int | None = None):
+        self._L = load()
+        self._h = _ctx()
+        rc = self._L.sc_create(int(device), int(precision), int(capacity), C.c_void_p(stream) if stream else None,
+                               C.byref(self._h))
+        if rc:
+            raise SandCrateError(self._L.sc_last_error(None).decode())
+        self.capacity = int(capacity)
+        self.precision = int(precision)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value is not None:
+            self._L.sc_destroy(self._h)
+            self._h = _ctx()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SandCrateError(self._L.sc_last_error(self._h).decode())
+
+    # ---- configuration ----
+    def set_params(self, **kw):
+        p = ScParams(*[float(kw[n]) for n in PARAM_FIELDS])
+        self._ck(self._L.sc_set_params(self._h, C.byref(p)))
+
+    def set_walls(self, segments, body_len, body_kin):
+        seg = _f64(segments, 4)
+        bl = np.ascontiguousarray(body_len, dtype=np.int32)
+        bk = _f64(body_kin, 5)
+        self._ck(self._L.sc_set_walls(self._h, _ptr(seg, _dp), seg.shape[0], _ptr(bl, _ip), _ptr(bk, _dp), bl.shape[0]))
+
+    def set_noise(self, mode: int, seed: int = 0):
+        self._ck(self._L.sc_set_noise(self._h, int(mode), C.c_uint64(seed)))
+
+    def set_tick(self, tick: int):
+        self._ck(self._L.sc_set_tick(self._h, C.c_uint64(tick)))
+
+    # ---- state ----
+    def set_state(self, pos, vel):
+        pos, vel = _f64(pos, 2), _f64(vel, 2)
+        assert pos.shape == vel.shape
+        self._ck(self._L.sc_set_state(self._h, _ptr(pos, _dp), _ptr(vel, _dp), pos.shape[0]))
+
+    def append_particles(self, pos, vel):
+        pos, vel = _f64(pos, 2), _f64(vel, 2)
+        assert pos.shape == vel.shape
+        self._ck(self._L.sc_append_particles(self._h, _ptr(pos, _dp), _ptr(vel, _dp), pos.shape[0]))
+
+    def particle_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self._L.sc_particle_count(self._h, C.byref(n)))
+        return n.value
+
+    def get_state(self, want_vel=True, want_pressure=True):
+        n = self.particle_count()
+        pos = np.empty((n, 2))
+        vel = np.empty((n, 2)) if want_vel else None
+        prs = np.empty(n) if want_pressure else None
+        m = C.c_int64()
+        self._ck(self._L.sc_get_state(self._h, _ptr(pos, _dp), _ptr(vel, _dp), _ptr(prs, _dp), n, C.byref(m)))
+        assert m.value == n
+        return pos, vel, prs
+
+    def get_uids(self):
+        n = self.particle_count()
+        uid = np.empty(n, np.uint32)
+        m = C.c_int64()
+        self._ck(self._L.sc_get_uids(self._h, _ptr(uid, _up), n, C.byref(m)))
+        return uid
+
+    # ---- step ----
+    def step(self, n: int = 1):
+        self._ck(self._L.sc_step_n(self._h, int(n)) if n != 1 else self._L.sc_step(self._h))
+
+    def step_begin(self):
+        n, k = C.c_int64(), C.c_int64()
+        self._ck(self._L.sc_step_begin(self._h, C.byref(n), C.byref(k)))
+        return n.value, k.value
+
+    def step_finish(self, noise=None):
+        if noise is not None:
+            noise = _f64(noise)
+        self._ck(self._L.sc_step_finish(self._h, _ptr(noise, _dp)))
+
+    def synchronize(self):
+        self._ck(self._L.sc_synchronize(self._h))
+
+    # ---- taps ----
+    def get_search(self, n: int):
+        pos = np.empty((n, 2))
+        rows = np.empty(n, np.int64)
+        order = np.empty(n, np.int64)
+        self._ck(self._L.sc_get_search(self._h, _ptr(pos, _dp), _ptr(rows, _lp), _ptr(order, _lp), n))
+        return pos, rows, order
+
+    def get_neighbors(self, n: int):
+        counts = np.empty(n, np.int32)
+        idx = np.empty((n, MAX_NEIGHBORS), np.int32)
+        self._ck(self._L.sc_get_neighbors(self._h, _ptr(counts, _ip), _ptr(idx, _ip), n))
+        return counts, idx
+
+    def get_tension(self, n: int):
+        t = np.empty((n, 2))
+        self._ck(self._L.sc_get_tension(self._h, _ptr(t, _dp), n))
+        return t
+
+    def get_wall_counts(self, n: int):
+        c = np.empty(n, np.int32)
+        self._ck(self._L.sc_get_wall_counts(self._h, _ptr(c, _ip), n))
+        return c
+
+    # ---- standalone layer-2 ops ----
+    def detect_particle_collisions(self, particles, diameter):
+        pts = _f64(particles, 2)
+        P = pts.shape[0]
+        rows = np.empty(P, np.int64)
+        order = np.empty(P, np.int64)
+        counts = np.empty(P, np.int32)
+        idx = np.empty((P, MAX_NEIGHBORS), np.int32)
+        self._ck(self._L.sc_detect_particle_collisions(self._h, _ptr(pts, _dp), P, float(diameter), _ptr(rows, _lp),
+                                                       _ptr(order, _lp), _ptr(counts, _ip), _ptr(idx, _ip)))
+        return rows, order, counts, idx
+
+    def points_to_segments_distance(self, p, segments):
+        p = _f64(p, 2)
+        seg = _f64(segments, 4)
+        near = np.empty((p.shape[0], seg.shape[0], 2))
+        dist = np.empty((p.shape[0], seg.shape[0]))
+        self._ck(self._L.sc_points_to_segments_distance(self._h, _ptr(p, _dp), p.shape[0], _ptr(seg, _dp), seg.shape[0],
+                                                        _ptr(near, _dp), _ptr(dist, _dp)))
+        return near, dist
+
+    # ---- measurement ----
+    def profile_enable(self, on: bool = True):
+        self._ck(self._L.sc_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        launches = np.zeros(PROFILE_SLOTS, np.int64)
+        ms = np.zeros(PROFILE_SLOTS)
+        self._ck(self._L.sc_profile_read(self._h, _ptr(launches, _lp), _ptr(ms, _dp), PROFILE_SLOTS))
+        out = {}
+        for i in range(PROFILE_SLOTS):
+            name = self._L.sc_profile_name(i).decode()
+            if name and launches[i]:
+                out[name] = {"launches": int(launches[i]), "ms": float(ms[i])}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self._L.sc_launch_count(self._h))
+
+
+def pad_segments(segments, pad):
+    """geometry_utils.py:146-172 through the C ABI (host arithmetic, no GPU needed)."""
+    seg = _f64(segments, 4)
+    out = np.empty((2 * seg.shape[0], 2, 2))
+    load().sc_pad_segments(_ptr(seg, _dp), seg.shape[0], float(pad), _ptr(out, _dp))
+    return out

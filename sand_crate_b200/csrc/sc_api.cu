@@ -1,0 +1,855 @@
+// sc_api.cu - context, launch orchestration and the C ABI declared in include/sandcrate.h.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see sand_crate_b200/build.py).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sc_sort.cuh"
+
+using namespace sc;
+
+static std::string g_create_error;
+
+enum Slot {
+    SLOT_CLEAR = 0, SLOT_PREPASS, SLOT_SCAN, SLOT_PLACE, SLOT_RANK_GATHER, SLOT_DENSITY, SLOT_FORCE, SLOT_COUNT,
+    SLOT_RANKMAP, SLOT_IO, SLOT_END
+};
+static const char *k_slot_names[SC_PROFILE_SLOTS] = {
+    "clear", "prepass_wall_key", "scan", "place", "rank_gather", "density", "force_integrate", "count_neighbors",
+    "rank_map", "io_scatter", "end_tick", "", "", "", "", ""};
+
+struct ProfEvent { int slot; cudaEvent_t e0, e1; };
+
+struct sc_ctx {
+    int device = 0, precision = 0;
+    int64_t cap = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    sc_params hp{};
+    bool params_set = false, walls_set = false;
+    DevParams dp{};
+    Grid grid{};
+    WallParams walls{};
+    int noise_mode = SC_NOISE_NONE;
+    uint64_t seed = 0, tick = 0;
+    // particle state: *_cur = current state (order left by the previous tick), *_srt = this tick's sorted gather
+    double2 *pos_cur = nullptr, *pos_srt = nullptr;
+    void *vel_cur = nullptr, *vel_srt = nullptr;
+    uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
+    uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
+    uint32_t *cell_start = nullptr; size_t cell_cap = 0;
+    uint32_t *bsum = nullptr; size_t bsum_cap = 0;
+    void *pressure = nullptr, *tension = nullptr;
+    uint32_t *wall_bits_cur = nullptr, *wall_bits_srt = nullptr, *wall_slot_cur = nullptr, *wall_slot_srt = nullptr;
+    double2 *wall_pre = nullptr;
+    Counters *cnt = nullptr;
+    uint32_t *rank_of_uid = nullptr; size_t uid_cap = 0;
+    uint32_t next_uid = 0;
+    uint32_t *count_by_rank = nullptr, *list_sorted = nullptr;
+    double *noise_dev = nullptr; size_t noise_cap = 0;
+    double2 *stage2 = nullptr; double *stage1 = nullptr;
+    int64_t n_host = 0;       // upper bound on the live count; exact when n_exact
+    bool n_exact = true;
+    bool in_step = false;     // between sc_step_begin and sc_step_finish
+    bool srt_valid = false;   // *_srt arrays hold the last tick's search state
+    bool lists_valid = false, rank_valid = false;
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfEvent> pending;
+    std::vector<cudaEvent_t> pool;
+    int64_t prof_launches[SC_PROFILE_SLOTS] = {0};
+    double prof_ms[SC_PROFILE_SLOTS] = {0};
+};
+
+static int fail(sc_ctx *c, const std::string &m) {
+    if (c) c->err = m; else g_create_error = m;
+    return 1;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +   \
+                                 std::to_string(__LINE__) + ")");                                       \
+    } while (0)
+#define CKR(expr)            \
+    do {                     \
+        int r_ = (expr);     \
+        if (r_) return r_;   \
+    } while (0)
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + SC_BLOCK - 1) / SC_BLOCK); }
+
+struct ProfScope {
+    sc_ctx *c; int slot; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(sc_ctx *c_, int slot_) : c(c_), slot(slot_) {
+        c->launches++;
+        if (!c->profiling) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->pool.empty()) { e = c->pool.back(); c->pool.pop_back(); } else cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get(); e1 = get();
+        cudaEventRecord(e0, c->stream);
+    }
+    ~ProfScope() {
+        if (!c->profiling) return;
+        cudaEventRecord(e1, c->stream);
+        c->pending.push_back({slot, e0, e1});
+    }
+};
+
+static int prof_flush(sc_ctx *ctx) {
+    if (ctx->pending.empty()) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &p : ctx->pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.e0, p.e1);
+        ctx->prof_ms[p.slot] += ms;
+        ctx->prof_launches[p.slot]++;
+        ctx->pool.push_back(p.e0);
+        ctx->pool.push_back(p.e1);
+    }
+    ctx->pending.clear();
+    return 0;
+}
+
+template <typename T> static int dev_alloc(sc_ctx *ctx, T **p, size_t count) {
+    CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    return 0;
+}
+static size_t real_size(const sc_ctx *c) { return c->precision == SC_PRECISION_F64 ? 8 : 4; }
+
+// ---------------------------------------------------------------------------------------------------------
+static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_min, int col_max) {
+    // one margin cell on every side so the 3x3 neighborhood never leaves the array
+    Grid g;
+    g.d = d;
+    g.row_min = row_min - 1;
+    g.col_min = col_min - 1;
+    const int64_t nrows = (int64_t)row_max - row_min + 3, ncols = (int64_t)col_max - col_min + 3;
+    if (nrows <= 0 || ncols <= 0 || nrows * ncols > (int64_t)1 << 31)
+        return fail(ctx, "cell grid too large: " + std::to_string(nrows) + " x " + std::to_string(ncols));
+    g.nrows = (int)nrows;
+    g.ncols = (int)ncols;
+    g.ncells = (uint32_t)(nrows * ncols);
+    const size_t need = (size_t)g.ncells + 2;
+    if (need > ctx->cell_cap) {
+        if (ctx->cell_start) CK(cudaFree(ctx->cell_start));
+        CKR(dev_alloc(ctx, &ctx->cell_start, need));
+        ctx->cell_cap = need;
+    }
+    const size_t nb = (size_t)(g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
+    const size_t nb2 = (size_t)(ctx->cap + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
+    const size_t needb = nb > nb2 ? nb : nb2;
+    if (needb > ctx->bsum_cap) {
+        if (ctx->bsum) CK(cudaFree(ctx->bsum));
+        CKR(dev_alloc(ctx, &ctx->bsum, needb));
+        ctx->bsum_cap = needb;
+    }
+    ctx->grid = g;
+    return 0;
+}
+
+static int refresh_dev_params(sc_ctx *ctx) {
+    const sc_params &h = ctx->hp;
+    DevParams &p = ctx->dp;
+    p.dt = h.dt; p.r = h.particle_radius; p.d = h.particle_radius * 2;  // crate.py:65-67
+    p.touch = h.particle_radius * 1.2;                                   // crate.py:229
+    p.decay = h.wall_collision_decay; p.amp = h.pressure_amplifier; p.ignored = h.ignored_pressure;
+    p.level = h.collider_noise_level; p.visc = h.viscosity; p.smooth = h.surface_smoothing;
+    p.target = h.target_pressure; p.gx = h.gravity_x; p.gy = h.gravity_y;
+    p.box_lo = -h.particle_radius; p.box_hi = 1 + h.particle_radius;     // crate.py:152
+    return 0;
+}
+
+extern "C" int sc_version(void) { return 1; }
+
+extern "C" const char *sc_last_error(const sc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int sc_create(int device, int precision, int64_t capacity, void *stream, sc_ctx **out) {
+    sc_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, "sc_create: out is NULL");
+    *out = nullptr;
+    if (precision != SC_PRECISION_F64 && precision != SC_PRECISION_MIXED) return fail(nullptr, "sc_create: bad precision");
+    if (capacity < 1 || capacity > ((int64_t)1 << 31) - 1) return fail(nullptr, "sc_create: capacity out of range");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, std::string("sc_create: no CUDA device (") + cudaGetErrorString(e) +
+                                 "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, "sc_create: bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10)
+        return fail(nullptr, "sc_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                 ", this build targets sm_100a only");
+    sc_ctx *c = new sc_ctx();
+    ctx = c;
+    c->device = device; c->precision = precision; c->cap = capacity;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
+    const size_t n = (size_t)capacity, rs = real_size(c);
+    int rc = 0;
+    rc |= dev_alloc(c, &c->pos_cur, n); rc |= dev_alloc(c, &c->pos_srt, n);
+    rc |= dev_alloc(c, (char **)&c->vel_cur, n * 2 * rs); rc |= dev_alloc(c, (char **)&c->vel_srt, n * 2 * rs);
+    rc |= dev_alloc(c, &c->uid_cur, n); rc |= dev_alloc(c, &c->uid_srt, n);
+    rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
+    rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
+    rc |= dev_alloc(c, (char **)&c->pressure, n * rs); rc |= dev_alloc(c, (char **)&c->tension, n * 2 * rs);
+    rc |= dev_alloc(c, &c->wall_bits_cur, n / 32 + 1); rc |= dev_alloc(c, &c->wall_bits_srt, n / 32 + 1);
+    rc |= dev_alloc(c, &c->wall_slot_cur, n); rc |= dev_alloc(c, &c->wall_slot_srt, n);
+    rc |= dev_alloc(c, &c->wall_pre, n);
+    rc |= dev_alloc(c, &c->cnt, 1);
+    rc |= dev_alloc(c, &c->count_by_rank, n + 1);
+    rc |= dev_alloc(c, &c->stage2, n); rc |= dev_alloc(c, &c->stage1, n);
+    if (rc) { g_create_error = c->err; sc_destroy(c); return 1; }
+    cudaMemsetAsync(c->cnt, 0, sizeof(Counters), c->stream);
+    c->walls.S = 0; c->walls.nbodies = 0;
+    *out = c;
+    return 0;
+}
+
+extern "C" void sc_destroy(sc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->pressure, c->tension,
+                    c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
+                    c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto e : c->pool) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int sc_set_params(sc_ctx *ctx, const sc_params *p) {
+    if (!ctx || !p) return fail(ctx, "sc_set_params: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    if (!(p->particle_radius > 0) || !(p->dt == p->dt)) return fail(ctx, "sc_set_params: particle_radius must be > 0");
+    const bool regrid = !ctx->params_set || p->particle_radius != ctx->hp.particle_radius;
+    if (regrid && ctx->in_step) return fail(ctx, "sc_set_params: radius change inside a split step");
+    ctx->hp = *p;
+    refresh_dev_params(ctx);
+    if (regrid) {
+        // live particles satisfy -r <= coord <= 1 + r (crate.py:152) and apply_hard_wall_fix moves by < r
+        const double d = ctx->dp.d, r = ctx->dp.r;
+        const int lo = (int)std::floor((-2 * r) / d) - 1, hi = (int)std::floor((1 + 2 * r) / d) + 1;
+        CKR(setup_grid(ctx, d, lo, hi, lo, hi));
+        ctx->srt_valid = false;
+        if (ctx->walls_set) sc_pad_segments(&ctx->walls.seg[0][0], ctx->walls.S, r, &ctx->walls.pad[0][0]);
+    }
+    ctx->params_set = true;
+    return 0;
+}
+
+extern "C" int sc_pad_segments(const double *segments, int S, double pad, double *padded) {
+    // geometry_utils.py:146-172.  Host code of this file is built with -ffp-contract=off.
+    for (int k = 0; k < S; ++k) {
+        const double ax = segments[4 * k], ay = segments[4 * k + 1], bx = segments[4 * k + 2], by = segments[4 * k + 3];
+        const double abx = bx - ax, aby = by - ay;
+        const double nx = aby, ny = -abx;
+        const double norm = std::sqrt(nx * nx + ny * ny);
+        const double ox = nx * pad / norm, oy = ny * pad / norm;
+        double *p1 = padded + 4 * k, *p2 = padded + 4 * (S + k);
+        p1[0] = ax + ox; p1[1] = ay + oy; p1[2] = bx + ox; p1[3] = by + oy;
+        p2[0] = bx - ox; p2[1] = by - oy; p2[2] = ax - ox; p2[3] = ay - oy;
+    }
+    return 0;
+}
+
+extern "C" int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const int32_t *body_len,
+                            const double *body_kin, int nbodies) {
+    if (!ctx) return fail(ctx, "sc_set_walls: NULL ctx");
+    if (S < 0 || S > SC_MAX_SEGMENTS) return fail(ctx, "sc_set_walls: more than SC_MAX_SEGMENTS segments");
+    if (nbodies < 0 || nbodies > SC_MAX_BODIES) return fail(ctx, "sc_set_walls: more than SC_MAX_BODIES bodies");
+    if (!ctx->params_set) return fail(ctx, "sc_set_walls: call sc_set_params first (padding needs the radius)");
+    WallParams &w = ctx->walls;
+    w.S = S; w.nbodies = nbodies;
+    int k = 0;
+    for (int b = 0; b < nbodies; ++b) {
+        for (int q = 0; q < body_len[b]; ++q) {
+            if (k >= S) return fail(ctx, "sc_set_walls: body_len does not sum to S");
+            w.seg_body[k++] = b;
+        }
+        for (int q = 0; q < 5; ++q) w.kin[b][q] = body_kin[5 * b + q];
+    }
+    if (k != S) return fail(ctx, "sc_set_walls: body_len does not sum to S");
+    if (S) std::memcpy(&w.seg[0][0], segments, sizeof(double) * 4 * (size_t)S);
+    sc_pad_segments(&w.seg[0][0], S, ctx->dp.r, &w.pad[0][0]);
+    ctx->walls_set = true;
+    return 0;
+}
+
+extern "C" int sc_set_noise(sc_ctx *ctx, int mode, uint64_t seed) {
+    if (!ctx) return fail(ctx, "sc_set_noise: NULL ctx");
+    if (mode < SC_NOISE_NONE || mode > SC_NOISE_HOST) return fail(ctx, "sc_set_noise: bad mode");
+    ctx->noise_mode = mode; ctx->seed = seed;
+    return 0;
+}
+extern "C" int sc_set_tick(sc_ctx *ctx, uint64_t tick) {
+    if (!ctx) return fail(ctx, "sc_set_tick: NULL ctx");
+    ctx->tick = tick;
+    return 0;
+}
+
+static int sync_count(sc_ctx *ctx) {
+    if (ctx->n_exact) return 0;
+    Counters h;
+    CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_host = h.n;
+    ctx->n_exact = true;
+    return 0;
+}
+
+static int upload_particles(sc_ctx *ctx, const double *pos, const double *vel, int64_t at, int64_t n) {
+    if (n == 0) return 0;
+    CK(cudaMemcpyAsync(ctx->pos_cur + at, pos, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->precision == SC_PRECISION_F64) {
+        CK(cudaMemcpyAsync((double2 *)ctx->vel_cur + at, vel, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice,
+                           ctx->stream));
+    } else {
+        CK(cudaMemcpyAsync(ctx->stage2, vel, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        ProfScope ps(ctx, SLOT_IO);
+        k_convert_vel_in<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(ctx->stage2, (float2 *)ctx->vel_cur + at,
+                                                                            (uint32_t)n);
+    }
+    {
+        ProfScope ps(ctx, SLOT_IO);
+        k_iota<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(ctx->uid_cur + at, ctx->next_uid, (uint32_t)n);
+    }
+    ctx->next_uid += (uint32_t)n;
+    const uint32_t newn = (uint32_t)(at + n);
+    CK(cudaMemcpyAsync(&ctx->cnt->n, &newn, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // host buffers are borrowed for the duration of the call only
+    ctx->n_host = at + n;
+    ctx->n_exact = true;
+    ctx->rank_valid = false;
+    return 0;
+}
+
+extern "C" int sc_set_state(sc_ctx *ctx, const double *pos, const double *vel, int64_t n) {
+    if (!ctx) return fail(ctx, "sc_set_state: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (n < 0 || n > ctx->cap) return fail(ctx, "sc_set_state: n exceeds capacity");
+    if (ctx->in_step) return fail(ctx, "sc_set_state: inside a split step");
+    ctx->next_uid = 0;
+    ctx->srt_valid = false; ctx->lists_valid = false;
+    const uint32_t zero = 0;
+    CK(cudaMemcpyAsync(&ctx->cnt->n, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_host = 0; ctx->n_exact = true;
+    return upload_particles(ctx, pos, vel, 0, n);
+}
+
+extern "C" int sc_append_particles(sc_ctx *ctx, const double *pos, const double *vel, int64_t n) {
+    if (!ctx) return fail(ctx, "sc_append_particles: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->in_step) return fail(ctx, "sc_append_particles: inside a split step");
+    if (n < 0) return fail(ctx, "sc_append_particles: n < 0");
+    CKR(sync_count(ctx));
+    if (ctx->n_host + n > ctx->cap) return fail(ctx, "sc_append_particles: capacity exceeded");
+    ctx->srt_valid = false; ctx->lists_valid = false;
+    return upload_particles(ctx, pos, vel, ctx->n_host, n);
+}
+
+extern "C" int sc_particle_count(sc_ctx *ctx, int64_t *n) {
+    if (!ctx || !n) return fail(ctx, "sc_particle_count: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    CKR(sync_count(ctx));
+    *n = ctx->n_host;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot) {
+    const unsigned nb = (n + SC_SCAN_TILE - 1) / SC_SCAN_TILE;
+    if (nb == 0) { CK(cudaMemsetAsync(a, 0, sizeof(uint32_t), ctx->stream)); return 0; }
+    if (nb + 1 > ctx->bsum_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->bsum) CK(cudaFree(ctx->bsum));
+        CKR(dev_alloc(ctx, &ctx->bsum, (size_t)nb + 1));
+        ctx->bsum_cap = (size_t)nb + 1;
+    }
+    ProfScope ps(ctx, slot);
+    k_scan_reduce<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum);
+    k_scan_sums<<<1, SC_BLOCK, 0, ctx->stream>>>(ctx->bsum, nb);
+    k_scan_apply<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum, nullptr);
+    ctx->launches += 2;
+    return 0;
+}
+
+// uid -> rank among live particles, for the uid array `uid` holding `cnt->n`-many... the live count is read from
+// n_ptr on the device.
+static int build_rank_map(sc_ctx *ctx, const uint32_t *uid, const uint32_t *n_ptr) {
+    const size_t need = (size_t)ctx->next_uid + 2;
+    if (need > ctx->uid_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->rank_of_uid) CK(cudaFree(ctx->rank_of_uid));
+        size_t cap = need * 2 > (size_t)ctx->cap + 2 ? need * 2 : (size_t)ctx->cap + 2;
+        CKR(dev_alloc(ctx, &ctx->rank_of_uid, cap));
+        ctx->uid_cap = cap;
+    }
+    CK(cudaMemsetAsync(ctx->rank_of_uid, 0, sizeof(uint32_t) * need, ctx->stream));
+    if (ctx->n_host > 0) {
+        ProfScope ps(ctx, SLOT_RANKMAP);
+        k_mark_alive<<<blocks_for(ctx->n_host), SC_BLOCK, 0, ctx->stream>>>(n_ptr, uid, ctx->rank_of_uid);
+    }
+    CKR(exclusive_scan(ctx, ctx->rank_of_uid, ctx->next_uid, SLOT_RANKMAP));
+    return 0;
+}
+
+static int require_ready(sc_ctx *ctx, const char *who) {
+    if (!ctx) return fail(ctx, std::string(who) + ": NULL ctx");
+    if (!ctx->params_set) return fail(ctx, std::string(who) + ": sc_set_params has not been called");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// remove -> walls -> keys -> sort -> gather
+template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
+    const int64_t n = ctx->n_host;
+    const Grid &g = ctx->grid;
+    {
+        ProfScope ps(ctx, SLOT_CLEAR);
+        k_begin_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt);
+        CK(cudaMemsetAsync(ctx->cell_start, 0, sizeof(uint32_t) * ((size_t)g.ncells + 1), ctx->stream));
+        CK(cudaMemsetAsync(ctx->wall_bits_cur, 0, sizeof(uint32_t) * ((size_t)ctx->cap / 32 + 1), ctx->stream));
+        CK(cudaMemsetAsync(ctx->wall_bits_srt, 0, sizeof(uint32_t) * ((size_t)ctx->cap / 32 + 1), ctx->stream));
+    }
+    if (n > 0) {
+        ProfScope ps(ctx, SLOT_PREPASS);
+        k_prepass<kStep><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot, ctx->cell_start,
+            ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre);
+    }
+    CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN));
+    if (n > 0) {
+        {
+            ProfScope ps(ctx, SLOT_PLACE);
+            k_place<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_key, ctx->slot, ctx->cell_start,
+                                                                 ctx->tmpidx);
+        }
+        ProfScope ps(ctx, SLOT_RANK_GATHER);
+        if (ctx->precision == SC_PRECISION_F64)
+            k_rank_gather<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, (double2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
+        else
+            k_rank_gather<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, (float2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
+    }
+    CK(cudaGetLastError());
+    ctx->srt_valid = true;
+    ctx->lists_valid = false;
+    ctx->rank_valid = false;
+    return 0;
+}
+
+// After enqueue_forces the uids of the sorted set live in uid_cur (pointer swap); inside a split step they are
+// still in uid_srt.
+static inline const uint32_t *sorted_uids(const sc_ctx *c) { return c->in_step ? c->uid_srt : c->uid_cur; }
+
+// rank map + neighbor counts (+ lists) for the sorted set
+static int enqueue_count(sc_ctx *ctx, const uint32_t *uid, bool want_lists) {
+    const int64_t n = ctx->n_host;
+    const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
+    if (!ctx->rank_valid) { CKR(build_rank_map(ctx, uid, n_ptr)); ctx->rank_valid = true; }
+    if (want_lists && !ctx->list_sorted) {
+        CKR(dev_alloc(ctx, &ctx->list_sorted, (size_t)ctx->cap * SC_MAX_NEIGHBORS));
+    }
+    CK(cudaMemsetAsync(&ctx->cnt->n_pairs, 0, sizeof(uint32_t), ctx->stream));
+    if (n > 0) {
+        ProfScope ps(ctx, SLOT_COUNT);
+        k_count_neighbors<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            ctx->cnt, ctx->grid, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, uid, ctx->rank_of_uid,
+            ctx->count_by_rank, want_lists ? ctx->list_sorted : nullptr);
+    }
+    CK(cudaGetLastError());
+    ctx->lists_valid = want_lists;
+    return 0;
+}
+
+__global__ void k_end_tick(Counters *cnt, const uint32_t *total) { cnt->n = *total; }
+
+static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
+    const int64_t n = ctx->n_host;
+    const Grid &g = ctx->grid;
+    DevParams dp = ctx->dp;
+    dp.noise_mode = (ctx->noise_mode != SC_NOISE_NONE && ctx->hp.collider_noise_level == 0.0) ? SC_NOISE_NONE
+                                                                                             : ctx->noise_mode;
+    dp.tick_key = tick_key(ctx->seed, ctx->tick);
+    if (n > 0) {
+        if (ctx->precision == SC_PRECISION_F64) {
+            {
+                ProfScope ps(ctx, SLOT_DENSITY);
+                k_density<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
+                    noise_off, ctx->rank_of_uid, (double *)ctx->pressure, (double2 *)ctx->tension);
+            }
+            ProfScope ps(ctx, SLOT_FORCE);
+            k_force<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                ctx->cnt, g, dp, ctx->walls, ctx->cell_start, ctx->pos_srt, (const double2 *)ctx->vel_srt,
+                ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev, noise_off, ctx->rank_of_uid,
+                (const double *)ctx->pressure, (const double2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt,
+                ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur);
+        } else {
+            {
+                ProfScope ps(ctx, SLOT_DENSITY);
+                k_density<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
+                    noise_off, ctx->rank_of_uid, (float *)ctx->pressure, (float2 *)ctx->tension);
+            }
+            ProfScope ps(ctx, SLOT_FORCE);
+            k_force<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                ctx->cnt, g, dp, ctx->walls, ctx->cell_start, ctx->pos_srt, (const float2 *)ctx->vel_srt,
+                ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev, noise_off, ctx->rank_of_uid,
+                (const float *)ctx->pressure, (const float2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt,
+                ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur);
+        }
+    }
+    {
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + g.ncells);
+    }
+    CK(cudaGetLastError());
+    // the new state (pos_cur, vel_cur) is in this tick's sorted order, whose uids are uid_srt
+    uint32_t *t = ctx->uid_cur; ctx->uid_cur = ctx->uid_srt; ctx->uid_srt = t;
+    ctx->tick += 1;  // crate.py:127
+    ctx->n_exact = false;
+    return 0;
+}
+
+extern "C" int sc_step(sc_ctx *ctx) {
+    CKR(require_ready(ctx, "sc_step"));
+    if (ctx->in_step) return fail(ctx, "sc_step: a split step is open");
+    if (ctx->noise_mode == SC_NOISE_HOST && ctx->hp.collider_noise_level != 0.0)
+        return fail(ctx, "sc_step: SC_NOISE_HOST needs sc_step_begin / sc_step_finish");
+    CKR(enqueue_search<true>(ctx));
+    return enqueue_forces(ctx, nullptr);
+}
+
+extern "C" int sc_step_n(sc_ctx *ctx, int nsteps) {
+    for (int i = 0; i < nsteps; ++i) CKR(sc_step(ctx));
+    return 0;
+}
+
+extern "C" int sc_step_begin(sc_ctx *ctx, int64_t *n_particles, int64_t *n_pairs) {
+    CKR(require_ready(ctx, "sc_step_begin"));
+    if (ctx->in_step) return fail(ctx, "sc_step_begin: a split step is already open");
+    CKR(enqueue_search<true>(ctx));
+    ctx->in_step = true;
+    CKR(enqueue_count(ctx, ctx->uid_srt, false));
+    Counters h;
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&total, ctx->cell_start + ctx->grid.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_particles) *n_particles = total;
+    if (n_pairs) *n_pairs = h.n_pairs;
+    return 0;
+}
+
+extern "C" int sc_step_finish(sc_ctx *ctx, const double *noise) {
+    CKR(require_ready(ctx, "sc_step_finish"));
+    if (!ctx->in_step) return fail(ctx, "sc_step_finish: no split step is open");
+    const uint32_t *noise_off = nullptr;
+    const bool host_noise = ctx->noise_mode == SC_NOISE_HOST && ctx->hp.collider_noise_level != 0.0;
+    if (host_noise) {
+        if (!noise) return fail(ctx, "sc_step_finish: SC_NOISE_HOST needs the noise array");
+        Counters h;
+        CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const size_t need = (size_t)h.n_pairs * 2;
+        if (need > ctx->noise_cap) {
+            if (ctx->noise_dev) CK(cudaFree(ctx->noise_dev));
+            CKR(dev_alloc(ctx, &ctx->noise_dev, need * 2 + 64));
+            ctx->noise_cap = need * 2 + 64;
+        }
+        if (need) CK(cudaMemcpyAsync(ctx->noise_dev, noise, sizeof(double) * need, cudaMemcpyHostToDevice, ctx->stream));
+        // CSR offsets in original index order (crate.py:165: `for particle_index in range(self.particle_count)`)
+        CKR(exclusive_scan(ctx, ctx->count_by_rank, (uint32_t)ctx->n_host, SLOT_COUNT));
+        noise_off = ctx->count_by_rank;
+        ctx->lists_valid = false;
+    }
+    ctx->in_step = false;
+    CKR(enqueue_forces(ctx, noise_off));
+    if (host_noise) CK(cudaStreamSynchronize(ctx->stream));  // `noise` is borrowed for the call only
+    return 0;
+}
+
+extern "C" int sc_synchronize(sc_ctx *ctx) {
+    if (!ctx) return fail(ctx, "sc_synchronize: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// readback (original index order)
+static int ensure_rank_for_current(sc_ctx *ctx) {
+    // the current state's uid array is uid_cur and its live count is cnt->n
+    if (!ctx->rank_valid) {
+        CKR(build_rank_map(ctx, sorted_uids(ctx), ctx->in_step ? ctx->cell_start + ctx->grid.ncells : &ctx->cnt->n));
+        ctx->rank_valid = true;
+    }
+    return 0;
+}
+
+extern "C" int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *pressure, int64_t cap, int64_t *n_out) {
+    if (!ctx) return fail(ctx, "sc_get_state: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->in_step) return fail(ctx, "sc_get_state: inside a split step");
+    CKR(sync_count(ctx));
+    const int64_t n = ctx->n_host;
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(ctx, "sc_get_state: buffer too small");
+    if (n == 0) return 0;
+    CKR(ensure_rank_for_current(ctx));
+    const uint32_t *n_ptr = &ctx->cnt->n;
+    const unsigned nb = blocks_for(n);
+    if (pos) {
+        { ProfScope ps(ctx, SLOT_IO);
+          k_scatter_vec2<double2><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, ctx->pos_cur, ctx->stage2); }
+        CK(cudaMemcpyAsync(pos, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (vel) {
+        { ProfScope ps(ctx, SLOT_IO);
+          if (ctx->precision == SC_PRECISION_F64)
+              k_scatter_vec2<double2><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const double2 *)ctx->vel_cur, ctx->stage2);
+          else
+              k_scatter_vec2<float2><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const float2 *)ctx->vel_cur, ctx->stage2); }
+        CK(cudaMemcpyAsync(vel, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (pressure) {
+        if (!ctx->srt_valid) {
+            CK(cudaMemsetAsync(ctx->stage1, 0, sizeof(double) * (size_t)n, ctx->stream));  // crate.py:26 before any tick
+        } else {
+            ProfScope ps(ctx, SLOT_IO);
+            if (ctx->precision == SC_PRECISION_F64)
+                k_scatter_scalar<double><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const double *)ctx->pressure, ctx->stage1);
+            else
+                k_scatter_scalar<float><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const float *)ctx->pressure, ctx->stage1);
+        }
+        CK(cudaMemcpyAsync(pressure, ctx->stage1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n_out) {
+    if (!ctx) return fail(ctx, "sc_get_uids: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->in_step) return fail(ctx, "sc_get_uids: inside a split step");
+    CKR(sync_count(ctx));
+    const int64_t n = ctx->n_host;
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(ctx, "sc_get_uids: buffer too small");
+    if (n == 0) return 0;
+    CKR(ensure_rank_for_current(ctx));
+    { ProfScope ps(ctx, SLOT_IO);
+      k_scatter_uid<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->uid_cur, ctx->rank_of_uid, (uint32_t *)ctx->stage1); }
+    CK(cudaMemcpyAsync(uid, ctx->stage1, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- taps --------------------------------------------------------------------------------------------------
+static int tap_prologue(sc_ctx *ctx, const char *who, int64_t cap, int64_t *n_out) {
+    if (!ctx) return fail(ctx, std::string(who) + ": NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->srt_valid) return fail(ctx, std::string(who) + ": no search state (call sc_step or sc_step_begin first)");
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->cell_start + ctx->grid.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if ((int64_t)total > cap) return fail(ctx, std::string(who) + ": buffer too small");
+    *n_out = total;
+    if (!ctx->rank_valid) {
+        CKR(build_rank_map(ctx, sorted_uids(ctx), ctx->cell_start + ctx->grid.ncells));
+        ctx->rank_valid = true;
+    }
+    return 0;
+}
+
+extern "C" int sc_get_search(sc_ctx *ctx, double *pos_search, int64_t *rows_sorted, int64_t *order, int64_t cap) {
+    int64_t n = 0;
+    CKR(tap_prologue(ctx, "sc_get_search", cap, &n));
+    if (n == 0) return 0;
+    const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
+    const uint32_t *uid = sorted_uids(ctx);
+    if (pos_search) {
+        { ProfScope ps(ctx, SLOT_IO);
+          k_scatter_vec2<double2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, uid, ctx->rank_of_uid, ctx->pos_srt, ctx->stage2); }
+        CK(cudaMemcpyAsync(pos_search, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (rows_sorted || order) {
+        long long *rows_d = (long long *)ctx->stage2, *order_d = rows_d + n;  // stage2 holds 2n 8-byte slots
+        { ProfScope ps(ctx, SLOT_IO);
+          k_tap_search<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->grid, ctx->pos_srt, uid, ctx->rank_of_uid, rows_d, order_d); }
+        if (rows_sorted) CK(cudaMemcpyAsync(rows_sorted, rows_d, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (order) CK(cudaMemcpyAsync(order, order_d, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sc_get_neighbors(sc_ctx *ctx, int32_t *counts, int32_t *idx, int64_t cap) {
+    int64_t n = 0;
+    CKR(tap_prologue(ctx, "sc_get_neighbors", cap, &n));
+    if (n == 0) return 0;
+    // (re)run the count kernel on the sorted set with list output; count_by_rank may hold CSR offsets after a
+    // host-noise finish, so it is always rebuilt here
+    CKR(enqueue_count(ctx, sorted_uids(ctx), true));
+    const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
+    if (counts) CK(cudaMemcpyAsync(counts, ctx->count_by_rank, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idx) {
+        int *idx_d = nullptr;
+        CK(cudaMalloc((void **)&idx_d, sizeof(int) * (size_t)n * SC_MAX_NEIGHBORS));
+        { ProfScope ps(ctx, SLOT_IO);
+          k_tap_lists<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, ctx->count_by_rank, ctx->list_sorted, idx_d); }
+        CK(cudaMemcpyAsync(idx, idx_d, sizeof(int) * (size_t)n * SC_MAX_NEIGHBORS, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(idx_d));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sc_get_tension(sc_ctx *ctx, double *tension, int64_t cap) {
+    int64_t n = 0;
+    CKR(tap_prologue(ctx, "sc_get_tension", cap, &n));
+    if (n == 0 || !tension) return 0;
+    if (ctx->in_step) return fail(ctx, "sc_get_tension: inside a split step");
+    const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
+    { ProfScope ps(ctx, SLOT_IO);
+      if (ctx->precision == SC_PRECISION_F64)
+          k_scatter_vec2<double2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const double2 *)ctx->tension, ctx->stage2);
+      else
+          k_scatter_vec2<float2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const float2 *)ctx->tension, ctx->stage2); }
+    CK(cudaMemcpyAsync(tension, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sc_get_wall_counts(sc_ctx *ctx, int32_t *counts, int64_t cap) {
+    int64_t n = 0;
+    CKR(tap_prologue(ctx, "sc_get_wall_counts", cap, &n));
+    if (n == 0 || !counts) return 0;
+    const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
+    { ProfScope ps(ctx, SLOT_IO);
+      k_tap_wall_counts<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->dp, ctx->walls, sorted_uids(ctx), ctx->rank_of_uid, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, (int *)ctx->stage1); }
+    CK(cudaMemcpyAsync(counts, ctx->stage1, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- standalone layer-2 ops ----------------------------------------------------------------------------------
+extern "C" int sc_detect_particle_collisions(sc_ctx *parent, const double *particles, int64_t P, double diameter,
+                                             int64_t *rows_sorted, int64_t *order, int32_t *counts, int32_t *idx) {
+    sc_ctx *ctx = parent;
+    if (!parent) return fail(parent, "sc_detect_particle_collisions: NULL ctx");
+    if (P < 0 || !(diameter > 0)) return fail(parent, "sc_detect_particle_collisions: bad arguments");
+    if (P == 0) return 0;
+    CK(cudaSetDevice(parent->device));
+    // a private context keeps the caller's simulation state untouched
+    sc_ctx *t = nullptr;
+    if (sc_create(parent->device, SC_PRECISION_F64, P, nullptr, &t)) return fail(parent, g_create_error);
+    auto bail = [&](int rc) { if (rc) parent->err = t->err; sc_destroy(t); return rc; };
+    ctx = t;
+    int rc = 0;
+    do {
+        t->hp = sc_params{}; t->hp.particle_radius = diameter / 2; t->params_set = true;
+        refresh_dev_params(t);
+        t->dp.d = diameter;  // r * 2 would round differently for odd diameters; the search only uses d
+        std::vector<double> zeros((size_t)P * 2, 0.0);
+        // grid bounds from the data
+        int hb[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+        int *db = nullptr;
+        if (cudaMalloc((void **)&db, sizeof(hb)) != cudaSuccess) { rc = fail(t, "cudaMalloc bounds"); break; }
+        cudaMemcpyAsync(db, hb, sizeof(hb), cudaMemcpyHostToDevice, t->stream);
+        // upload without a grid yet
+        t->grid.d = diameter;
+        if ((rc = upload_particles(t, particles, zeros.data(), 0, P))) { cudaFree(db); break; }
+        k_cell_bounds<<<blocks_for(P), SC_BLOCK, 0, t->stream>>>(t->pos_cur, (uint32_t)P, diameter, db);
+        cudaMemcpyAsync(hb, db, sizeof(hb), cudaMemcpyDeviceToHost, t->stream);
+        cudaStreamSynchronize(t->stream);
+        cudaFree(db);
+        if ((rc = setup_grid(t, diameter, hb[0], hb[1], hb[2], hb[3]))) break;
+        if ((rc = enqueue_search<false>(t))) break;
+        t->in_step = true;  // sorted uids are in uid_srt
+        int64_t n = 0;
+        if ((rc = tap_prologue(t, "sc_detect_particle_collisions", P, &n))) break;
+        if ((rc = sc_get_search(t, nullptr, rows_sorted, order, P))) break;
+        if ((rc = sc_get_neighbors(t, counts, idx, P))) break;
+    } while (0);
+    parent->launches += t->launches;
+    return bail(rc);
+}
+
+extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int64_t P, const double *segments, int S,
+                                              double *nearest, double *dist) {
+    if (!ctx) return fail(ctx, "sc_points_to_segments_distance: NULL ctx");
+    if (P < 0 || S < 0) return fail(ctx, "sc_points_to_segments_distance: bad arguments");
+    if (P == 0 || S == 0) return 0;
+    if (P * (int64_t)S > ((int64_t)1 << 31) - 1) return fail(ctx, "sc_points_to_segments_distance: P*S too large");
+    CK(cudaSetDevice(ctx->device));
+    double2 *dp = nullptr; double *ds = nullptr, *dn = nullptr, *dd = nullptr;
+    CK(cudaMalloc((void **)&dp, sizeof(double2) * (size_t)P));
+    CK(cudaMalloc((void **)&ds, sizeof(double) * 4 * (size_t)S));
+    CK(cudaMalloc((void **)&dn, sizeof(double) * 2 * (size_t)P * S));
+    CK(cudaMalloc((void **)&dd, sizeof(double) * (size_t)P * S));
+    CK(cudaMemcpyAsync(dp, p, sizeof(double2) * (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ds, segments, sizeof(double) * 4 * (size_t)S, cudaMemcpyHostToDevice, ctx->stream));
+    { ProfScope ps(ctx, SLOT_IO);
+      k_points_segments<<<blocks_for(P * S), SC_BLOCK, 0, ctx->stream>>>(dp, (uint32_t)P, ds, S, dn, dd); }
+    if (nearest) CK(cudaMemcpyAsync(nearest, dn, sizeof(double) * 2 * (size_t)P * S, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dist) CK(cudaMemcpyAsync(dist, dd, sizeof(double) * (size_t)P * S, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    cudaFree(dp); cudaFree(ds); cudaFree(dn); cudaFree(dd);
+    return 0;
+}
+
+// ---- measurement -------------------------------------------------------------------------------------------
+extern "C" int sc_profile_enable(sc_ctx *ctx, int on) {
+    if (!ctx) return fail(ctx, "sc_profile_enable: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    CKR(prof_flush(ctx));
+    ctx->profiling = on != 0;
+    if (on) for (int i = 0; i < SC_PROFILE_SLOTS; ++i) { ctx->prof_launches[i] = 0; ctx->prof_ms[i] = 0; }
+    return 0;
+}
+extern "C" int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int slots) {
+    if (!ctx) return fail(ctx, "sc_profile_read: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    CKR(prof_flush(ctx));
+    for (int i = 0; i < slots && i < SC_PROFILE_SLOTS; ++i) {
+        if (launches) launches[i] = ctx->prof_launches[i];
+        if (ms) ms[i] = ctx->prof_ms[i];
+    }
+    return 0;
+}
+extern "C" const char *sc_profile_name(int slot) { return (slot >= 0 && slot < SC_PROFILE_SLOTS) ? k_slot_names[slot] : ""; }
+extern "C" int64_t sc_launch_count(const sc_ctx *ctx) { return ctx ? ctx->launches : 0; }

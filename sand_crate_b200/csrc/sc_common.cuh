@@ -1,0 +1,114 @@
+// sc_common.cuh - shared device-side definitions for the SandCrate particle step on sm_100a.
+//
+// Everything here restates ONE reference tick (David-Taub/sand_crate src/crate/crate.py:91-129) as per-particle
+// device functions.  The file is compiled into two translation units:
+//   sc_kernels_f64.cu  (-fmad=false)  Real = double: NumPy never fuses multiply-add, so neither may we
+//   sc_kernels_f32.cu                 Real = float : production mode, positions stay fp64 in HBM
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sandcrate.h"
+
+#define SC_INVALID_CELL 0xFFFFFFFFu
+#define SC_BLOCK 256
+
+namespace sc {
+
+// uniform cell grid with cell edge = one particle diameter; row = floor(y / d) is the reference's strip index
+// (collision_detector.py:126), col = floor(x / d) is ours (monotone in x, so a cell-major order
+// (row, col, x, uid) is the same permutation as np.lexsort((x, row)), collision_detector.py:127).
+struct Grid {
+    double d;          // diameter
+    int row_min;       // cell row index = row - row_min, clamped to [1, nrows - 2]
+    int col_min;
+    int nrows;
+    int ncols;
+    uint32_t ncells;
+};
+
+struct DevParams {
+    double dt, r, d, touch;  // touch = r * 1.2 (crate.py:229)
+    double decay, amp, ignored, level, visc, smooth, target, gx, gy;
+    double box_lo, box_hi;   // -r, 1 + r  (crate.py:152)
+    int noise_mode;
+    uint64_t tick_key;
+};
+
+struct WallParams {
+    int S;
+    int nbodies;
+    double seg[SC_MAX_SEGMENTS][4];       // ax, ay, bx, by                       (crate.py:69-71)
+    double pad[2 * SC_MAX_SEGMENTS][4];   // pad_segments(segments, r)            (geometry_utils.py:146-172)
+    int seg_body[SC_MAX_SEGMENTS];
+    double kin[SC_MAX_BODIES][5];         // vcx, vcy, omega, posx, posy          (rigid_body.py:18-34)
+};
+
+// device-resident counters, zeroed/updated on the stream (no host round trip in the step)
+struct Counters {
+    uint32_t n;          // live particles at the start of the tick (= after the previous tick's removal)
+    uint32_t n_removed;  // removed this tick
+    uint32_t n_wall;     // particles touching a wall this tick
+    uint32_t n_pairs;    // sum K_i (filled by the count kernel)
+    uint32_t overflow;   // capacity problems seen on the device
+    uint32_t pad_[3];
+};
+
+// ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+__host__ __device__ inline uint64_t tick_key(uint64_t seed, uint64_t tick) {
+    return mix64(seed * 0x9E3779B97F4A7C15ULL + tick);
+}
+__device__ inline void pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j, uint32_t &hx, uint32_t &hy) {
+    const uint64_t h = mix64((((uint64_t)uid_i << 32) | (uint64_t)uid_j) ^ tkey);
+    hx = (uint32_t)(h >> 32);
+    hy = (uint32_t)(h & 0xffffffffu);
+}
+
+// ---- geometry_utils.py:7-39 for one (point, segment) -----------------------------------------------------
+__device__ inline double point_segment(double px, double py, double ax, double ay, double bx, double by,
+                                     double &cx, double &cy) {
+    const double abx = bx - ax, aby = by - ay;
+    const double apx = px - ax, apy = py - ay;
+    const double rate = (apx * abx + apy * aby) / (abx * abx + aby * aby);
+    double t = rate;  // np.clip(rate, 0, 1), NaN propagates
+    if (t < 0) t = 0;
+    if (t > 1) t = 1;
+    cx = abx * t + ax;
+    cy = aby * t + ay;
+    const double dx = cx - px, dy = cy - py;
+    return sqrt(dx * dx + dy * dy);
+}
+
+__device__ inline double sign_np(double v) {  // np.sign
+    if (v > 0) return 1.0;
+    if (v < 0) return -1.0;
+    if (v == 0) return 0.0;
+    return v;
+}
+__device__ inline double orientation(double px, double py, double qx, double qy, double rx, double ry) {
+    return sign_np(((qy - py) * (rx - qx)) - ((qx - px) * (ry - qy)));  // geometry_utils.py:212-222
+}
+
+// cell of a position; NaN / out-of-grid coordinates are clamped into the margin cells
+__device__ inline uint32_t cell_of(const Grid &g, double x, double y, int &row_out) {
+    const double fr = floor(y / g.d), fc = floor(x / g.d);
+    int row = (fr >= -2.0e9 && fr <= 2.0e9) ? (int)fr : 0;
+    int col = (fc >= -2.0e9 && fc <= 2.0e9) ? (int)fc : 0;
+    row_out = row;
+    int cr = row - g.row_min, cc = col - g.col_min;
+    cr = cr < 1 ? 1 : (cr > g.nrows - 2 ? g.nrows - 2 : cr);
+    cc = cc < 1 ? 1 : (cc > g.ncols - 2 ? g.ncols - 2 : cc);
+    return (uint32_t)cr * (uint32_t)g.ncols + (uint32_t)cc;
+}
+
+// total order used inside a cell: x ascending (NaN last, like np.lexsort), ties by uid (lexsort is stable and
+// original index order == uid order)
+__device__ inline bool x_less(double a, double b) { return a < b || (b != b && a == a); }
+
+}  // namespace sc

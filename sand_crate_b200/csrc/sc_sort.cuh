@@ -1,0 +1,339 @@
+// sc_sort.cuh - precision-independent kernels of the step: wall pre-pass + cell keys (K0/K1), exclusive scan,
+// counting-sort placement, in-cell rank + gather (K2/K3), neighbor count/list taps and the uid -> rank map.
+// All position arithmetic here is fp64 without FMA contraction, so cell keys, sorted order and neighbor lists
+// are bit-identical to the reference's in BOTH precision modes.
+#pragma once
+#include "sc_pair.cuh"
+
+namespace sc {
+
+// ------------------------------------------------------------------------------------------------------------
+// K0 + K1.  One thread per particle in the order the previous tick left them (that order is the previous
+// tick's sorted order, so neighbouring threads touch neighbouring cells).
+//   kStep = true : remove_particles (crate.py:149-159), calc_virtual_colliders + apply_hard_wall_fix
+//                  (crate.py:213-243, 202-211), then the cell key
+//   kStep = false: cell key only (standalone detect_particle_collisions)
+template <bool kStep>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
+          double2 *__restrict__ pos, uint32_t *__restrict__ cell_key, uint32_t *__restrict__ slot,
+          uint32_t *__restrict__ cell_count, uint32_t *__restrict__ wall_bits, uint32_t *__restrict__ wall_slot,
+          double2 *__restrict__ wall_pre) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt->n) return;
+    double2 p = pos[i];
+    if (kStep) {
+        const bool out = (p.x < P.box_lo) | (p.x > P.box_hi) | (p.y < P.box_lo) | (p.y > P.box_hi);
+        if (out) {
+            cell_key[i] = SC_INVALID_CELL;
+            atomicAdd(&cnt->n_removed, 1u);
+            return;
+        }
+        int V = 0;
+        double sx = 0, sy = 0;
+        for (int q = 0; q < W.S; ++q) {
+            double cx, cy;
+            const double dist = point_segment(p.x, p.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy);
+            if (dist <= P.touch) {
+                const double vcx = (p.x - cx) * 2, vcy = (p.y - cy) * 2;  // crate.py:234
+                double rel = P.r / sqrt(vcx * vcx + vcy * vcy);            // crate.py:206
+                if (rel < 0.5) rel = 0.5;
+                const double ex = vcx * (rel - 0.5), ey = vcy * (rel - 0.5);
+                if (V == 0) { sx = ex; sy = ey; } else { sx += ex; sy += ey; }
+                ++V;
+            }
+        }
+        if (V > 0) {
+            const uint32_t ws = atomicAdd(&cnt->n_wall, 1u);
+            wall_pre[ws] = p;  // contacts are re-derived from this position by the force kernel
+            wall_slot[i] = ws;
+            atomicOr(&wall_bits[i >> 5], 1u << (i & 31));
+            p.x += sx;
+            p.y += sy;
+            pos[i] = p;
+        }
+    }
+    int row;
+    const uint32_t c = cell_of(g, p.x, p.y, row);
+    cell_key[i] = c;
+    slot[i] = atomicAdd(&cell_count[c], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply)
+#define SC_SCAN_ITEMS 8
+#define SC_SCAN_TILE (SC_BLOCK * SC_SCAN_ITEMS)
+
+__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
+    __shared__ uint32_t warp_sums[SC_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < SC_BLOCK / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SC_BLOCK / 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < SC_BLOCK / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    total = warp_sums[SC_BLOCK / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) k_scan_reduce(const uint32_t *__restrict__ a, uint32_t n,
+                                                         uint32_t *__restrict__ bsum) {
+    const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < SC_SCAN_ITEMS; ++q)
+        if (base + q < n) v += a[base + q];
+    uint32_t total;
+    block_exclusive_scan(v, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) k_scan_sums(uint32_t *__restrict__ bsum, uint32_t nb) {
+    // single block: each thread scans a contiguous chunk
+    const uint32_t per = (nb + SC_BLOCK - 1) / SC_BLOCK;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, nb);
+    uint32_t v = 0;
+    for (uint32_t q = b0; q < b1; ++q) v += bsum[q];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(v, total);
+    for (uint32_t q = b0; q < b1; ++q) {
+        const uint32_t t = bsum[q];
+        bsum[q] = run;
+        run += t;
+    }
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) k_scan_apply(uint32_t *__restrict__ a, uint32_t n,
+                                                        const uint32_t *__restrict__ bsum,
+                                                        uint32_t *__restrict__ n_out) {
+    const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
+    uint32_t item[SC_SCAN_ITEMS];
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
+        item[q] = (base + q < n) ? a[base + q] : 0;
+        v += item[q];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(v, total) + bsum[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
+        if (base + q < n) a[base + q] = run;
+        run += item[q];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SC_BLOCK - 1) {
+        a[n] = run;  // grand total (all out-of-range items are 0)
+        if (n_out) *n_out = run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: counting-sort placement.  The arrival slot inside a cell came from an atomic, so the order inside a cell
+// is arbitrary here; k_rank_gather makes it deterministic.
+__global__ void __launch_bounds__(SC_BLOCK)
+k_place(const Counters *__restrict__ cnt, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ slot,
+        const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ tmpidx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt->n) return;
+    const uint32_t c = cell_key[i];
+    if (c == SC_INVALID_CELL) return;
+    tmpidx[cell_start[c] + slot[i]] = i;
+}
+
+// K3: rank inside the cell by (x, uid) and gather the particle record to its final sorted position.
+// Produces exactly np.lexsort((x, floor(y / d))) (collision_detector.py:127) as the concatenation of cells.
+template <typename Real>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ tmpidx,
+              const uint32_t *__restrict__ cell_key, const double2 *__restrict__ pos,
+              const typename Vec2<Real>::type *__restrict__ vel, const uint32_t *__restrict__ uid,
+              const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
+              double2 *__restrict__ pos_s, typename Vec2<Real>::type *__restrict__ vel_s,
+              uint32_t *__restrict__ uid_s, uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
+              uint32_t *__restrict__ wall_slot_s) {
+    const uint32_t n = cell_start[g.ncells];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t i = tmpidx[t];
+    const uint32_t c = cell_key[i];
+    const uint32_t beg = cell_start[c], end = cell_start[c + 1];
+    const double2 p = pos[i];
+    const uint32_t u = uid[i];
+    uint32_t rank = 0;
+    for (uint32_t m = beg; m < end; ++m) {
+        if (m == t) continue;
+        const uint32_t j = tmpidx[m];
+        const double xj = pos[j].x;
+        const uint32_t uj = uid[j];
+        rank += (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < u)) ? 1u : 0u;
+    }
+    const uint32_t f = beg + rank;
+    pos_s[f] = p;
+    vel_s[f] = vel[i];
+    uid_s[f] = u;
+    cell_key_s[f] = c;
+    if ((wall_bits[i >> 5] >> (i & 31)) & 1u) {
+        wall_slot_s[f] = wall_slot[i];
+        atomicOr(&wall_bits_s[f >> 5], 1u << (f & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// uid -> rank among live particles (= the reference's row index, crate.py:146-159)
+__global__ void __launch_bounds__(SC_BLOCK)
+k_mark_alive(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid, uint32_t *__restrict__ alive) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    alive[uid[s]] = 1u;
+}
+
+// neighbor counts (and optionally lists, as sorted indices) - the parity tap and the SC_NOISE_HOST split step
+__global__ void __launch_bounds__(SC_BLOCK)
+k_count_neighbors(Counters *__restrict__ cnt, Grid g, const uint32_t *__restrict__ cell_start,
+                  const double2 *__restrict__ pos, const uint32_t *__restrict__ cell_key,
+                  const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
+                  uint32_t *__restrict__ count_by_rank, uint32_t *__restrict__ list_sorted) {
+    const uint32_t n = cell_start[g.ncells];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double2 ps = pos[s];
+    int k = 0;
+    const int K = for_each_neighbor(s, ps, cell_key[s], g, cell_start, pos, [&](uint32_t j, double2) {
+        if (list_sorted) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = j;
+        ++k;
+    });
+    count_by_rank[rank_of_uid[uid[s]]] = (uint32_t)K;
+    atomicAdd(&cnt->n_pairs, (uint32_t)K);
+}
+
+// ---- scatter from sorted order to original (rank) order for host-visible arrays -------------------------------
+template <typename T2>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_scatter_vec2(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
+               const uint32_t *__restrict__ rank_of_uid, const T2 *__restrict__ src, double2 *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    const T2 v = src[s];
+    double2 o;
+    o.x = (double)v.x; o.y = (double)v.y;
+    dst[rank_of_uid[uid[s]]] = o;
+}
+template <typename T>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_scatter_scalar(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
+                 const uint32_t *__restrict__ rank_of_uid, const T *__restrict__ src, double *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    dst[rank_of_uid[uid[s]]] = (double)src[s];
+}
+__global__ void __launch_bounds__(SC_BLOCK)
+k_scatter_uid(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
+              const uint32_t *__restrict__ rank_of_uid, uint32_t *__restrict__ dst) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    dst[rank_of_uid[uid[s]]] = uid[s];
+}
+
+// search taps: rows_sorted[s] = floor(y / d) of the particle at sorted index s, order[s] = its original index
+__global__ void __launch_bounds__(SC_BLOCK)
+k_tap_search(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__restrict__ pos,
+             const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
+             long long *__restrict__ rows_sorted, long long *__restrict__ order) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    rows_sorted[s] = (long long)floor(pos[s].y / g.d);
+    order[s] = (long long)rank_of_uid[uid[s]];
+}
+
+// neighbor lists in original index order holding original indices, -1 padded (collision_detector.py:46-48)
+__global__ void __launch_bounds__(SC_BLOCK)
+k_tap_lists(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
+            const uint32_t *__restrict__ rank_of_uid, const uint32_t *__restrict__ count_by_rank,
+            const uint32_t *__restrict__ list_sorted, int *__restrict__ idx_out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    const uint32_t r = rank_of_uid[uid[s]];
+    const uint32_t K = count_by_rank[r];
+    for (uint32_t k = 0; k < SC_MAX_NEIGHBORS; ++k)
+        idx_out[(size_t)r * SC_MAX_NEIGHBORS + k] =
+            k < K ? (int)rank_of_uid[uid[list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k]]] : -1;
+}
+
+// wall contact counts V_i (crate.py:229-232) in original order
+__global__ void __launch_bounds__(SC_BLOCK)
+k_tap_wall_counts(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
+                  const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
+                  const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
+                  const double2 *__restrict__ wall_pre, int *__restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    int V = 0;
+    if ((wall_bits[s >> 5] >> (s & 31)) & 1u) {
+        const double2 pre = wall_pre[wall_slot[s]];
+        for (int q = 0; q < W.S; ++q) {
+            double cx, cy;
+            if (point_segment(pre.x, pre.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy) <= P.touch) ++V;
+        }
+    }
+    out[rank_of_uid[uid[s]]] = V;
+}
+
+// geometry_utils.py:7-39 as a dense P x S op (the reference's own unit test pins this one)
+__global__ void __launch_bounds__(SC_BLOCK)
+k_points_segments(const double2 *__restrict__ p, uint32_t P_, const double *__restrict__ seg, int S,
+                  double *__restrict__ nearest, double *__restrict__ dist) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P_ * (uint32_t)S) return;
+    const uint32_t i = t / (uint32_t)S, q = t % (uint32_t)S;
+    double cx, cy;
+    dist[t] = point_segment(p[i].x, p[i].y, seg[4 * q], seg[4 * q + 1], seg[4 * q + 2], seg[4 * q + 3], cx, cy);
+    nearest[2 * (size_t)t] = cx;
+    nearest[2 * (size_t)t + 1] = cy;
+}
+
+// min / max cell coordinates of an arbitrary point set (standalone detect_particle_collisions)
+__global__ void __launch_bounds__(SC_BLOCK)
+k_cell_bounds(const double2 *__restrict__ pos, uint32_t n, double d, int *__restrict__ bounds /* rmin rmax cmin cmax */) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double fr = floor(pos[i].y / d), fc = floor(pos[i].x / d);
+    const int r = (fr >= -2.0e9 && fr <= 2.0e9) ? (int)fr : 0, c = (fc >= -2.0e9 && fc <= 2.0e9) ? (int)fc : 0;
+    atomicMin(&bounds[0], r); atomicMax(&bounds[1], r);
+    atomicMin(&bounds[2], c); atomicMax(&bounds[3], c);
+}
+
+__global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = base + i;
+}
+
+__global__ void k_begin_tick(Counters *cnt) {
+    cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_convert_vel_in(const double2 *__restrict__ src, typename Vec2<Real>::type *__restrict__ dst, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename Vec2<Real>::type v;
+    v.x = (Real)src[i].x; v.y = (Real)src[i].y;
+    dst[i] = v;
+}
+
+}  // namespace sc

@@ -1,0 +1,68 @@
+"""Synthetic benchmark scenes (BASELINE.json `configs[2:]`).
+
+The reference's world is hard-wired to the unit square (crate.py:152), so large particle counts mean a small
+particle diameter; `dt` is scaled with it so that `v * dt / d` keeps the ratio of the shipped configs.  All scenes:
+closed unit box (the four fixed segments of wave_machine.yaml:35-40), no sources, no motored bodies, the
+coefficients of wave_machine.yaml:10-22, square lattice at 0.75 * d spacing (the reference's own bulk rest spacing
+is 0.67-0.84 * d) with +-5 % uniform jitter from RandomState(42), zero initial velocity, gravity +y (y = 1 is the
+floor).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .load_config import WorldConfig
+
+BASE_COEFFICIENTS = {
+    "dt": 0.002, "particle_radius": 0.005, "wall_collision_decay": 0.2, "spring_overlap_balance": 0.5,
+    "spring_amplifier": 100, "pressure_amplifier": 30, "ignored_pressure": 0.3, "collider_noise_level": 0.1,
+    "viscosity": 8, "max_particles": 0, "surface_smoothing": 100, "target_pressure": -2, "gravity": [0, 9.8],
+}
+UNIT_BOX = {"fixed": {"name": "edge", "segments": [
+    [[0.0, 0.0], [0.0, 1.0]], [[0.0, 0.0], [1.0, 0.0]], [[1.0, 0.0], [1.0, 1.0]], [[0.0, 1.0], [1.0, 1.0]]]}}
+LATTICE_FRACTION = 0.75
+
+
+def _world(n: int, diameter: float, **overrides) -> WorldConfig:
+    coeffs = dict(BASE_COEFFICIENTS)
+    coeffs["particle_radius"] = diameter / 2
+    coeffs["dt"] = 0.002 * (diameter / 0.01)
+    coeffs["max_particles"] = int(n)
+    coeffs.update(overrides)
+    return WorldConfig(rigid_bodies=[UNIT_BOX], particle_sources=[], coefficients=coeffs)
+
+
+def _lattice(n: int, x0: float, x1: float, y_floor: float, spacing: float, seed: int) -> np.ndarray:
+    """n points on a square lattice filling [x0, x1] row by row upwards from y_floor, jittered by +-5 %."""
+    nx = max(int(math.floor((x1 - x0) / spacing)), 1)
+    ny = (n + nx - 1) // nx
+    ix = np.arange(nx, dtype=np.float64)
+    iy = np.arange(ny, dtype=np.float64)
+    xs = np.tile(x0 + (ix + 0.5) * spacing, ny)[:n]
+    ys = np.repeat(y_floor - (iy + 0.5) * spacing, nx)[:n]
+    rs = np.random.RandomState(seed)
+    pts = np.stack((xs, ys), axis=1)
+    pts += (rs.rand(n, 2) - 0.5) * (0.1 * spacing)
+    return pts
+
+
+def dam_break(n: int, seed: int = 42, width: float = 0.4, height: float = 0.8, **overrides):
+    """A column of liquid against the left wall that collapses under gravity.
+    1M on one GPU: d ~ 7.5e-4, ~1330 cell rows; 64M: width 0.5, height 1.0 -> d ~ 1.2e-4."""
+    spacing = math.sqrt(width * height / n)
+    d = spacing / LATTICE_FRACTION
+    pts = _lattice(n, d, width, 1.0 - d, spacing, seed)
+    return _world(n, d, **overrides), pts, np.zeros_like(pts)
+
+
+def box_fill(n: int, seed: int = 42, **overrides):
+    """The whole box filled at rest density (uniform load, the multi-GPU strip-decomposition case)."""
+    spacing = math.sqrt(1.0 / n)
+    d = spacing / LATTICE_FRACTION
+    pts = _lattice(n, d, 1.0 - d, 1.0 - d, spacing * (1.0 - 2 * d), seed)
+    return _world(n, d, **overrides), pts, np.zeros_like(pts)
+
+
+SCENES = {"dam_break": dam_break, "box_fill": box_fill}

@@ -1,0 +1,321 @@
+"""GPU parity tests (pytest -m gpu, B200 only).  Everything goes through the C ABI (sand_crate_b200._lib.Context ->
+libsandcrate.so); the oracle is only the checker.
+
+Bars:
+  * cell rows, sorted order, neighbor lists (order + 20-trim): bit-exact, both precision modes
+  * fp64 parity mode: positions, velocities, pressures, surface normals bit-exact per step
+  * mixed mode (fp64 positions, fp32 forces): per step from the same inputs,
+      max|dv| <= 1e-5 * max(max|v|, 1)   and   max|dpos| <= 1e-5 * d
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, neighbor_case_tags, params_from_coeffs, step_goldens, world_from_freerun
+from oracle import oracle as O
+from sand_crate_b200 import Crate, _lib
+from sand_crate_b200.scenes import box_fill, dam_break
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_F32 = 1e-5
+
+
+def make_ctx(g, precision, noise_mode, capacity=None, seed=0):
+    ctx = _lib.Context(capacity or max(len(g["pos_in"]), 1), precision)
+    ctx.set_params(**params_from_coeffs(g["coeffs"]))
+    ctx.set_walls(g["segments"], g["body_len"], g["body_kin"])
+    ctx.set_noise(noise_mode, seed)
+    ctx.set_state(g["pos_in"], g["vel_in"])
+    return ctx
+
+
+# ---- layer-2 functions ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", neighbor_case_tags())
+def test_detect_particle_collisions_bit_exact(tag):
+    g = golden("neighbors_cases.npz")
+    ctx = _lib.Context(16)
+    rows, order, counts, idx = ctx.detect_particle_collisions(g[f"{tag}__pts"], float(g[f"{tag}__d"]))
+    assert np.array_equal(rows, g[f"{tag}__rows"])
+    assert np.array_equal(order, g[f"{tag}__order"])
+    assert np.array_equal(counts, g[f"{tag}__counts"])
+    assert np.array_equal(idx, g[f"{tag}__idx"])
+
+
+def test_points_to_segments_distance_bit_exact():
+    g = golden("geometry_cases.npz")
+    ctx = _lib.Context(16)
+    for k in ("row", "rnd"):
+        near, dist = ctx.points_to_segments_distance(g[f"{k}_p"], g[f"{k}_segs"])
+        assert np.array_equal(near, g[f"{k}_near"]) and np.array_equal(dist, g[f"{k}_dist"])
+    _, dist = ctx.points_to_segments_distance(g["row_p"], g["row_segs"])
+    for i in range(5):
+        for j in range(35):
+            assert dist[j, i] == abs(j - i)  # the reference's own known-answer test (test_distance.py:16-25)
+
+
+# ---- one tick against the recorded reference ---------------------------------------------------------------
+@pytest.mark.parametrize("name", step_goldens())
+def test_step_f64_reference_noise_bit_exact(name):
+    g = golden(name)
+    ctx = make_ctx(g, _lib.PRECISION_F64, _lib.NOISE_HOST)
+    n, n_pairs = ctx.step_begin()
+    assert n == len(g["pos_search"]) and n_pairs == len(g["noise"])
+    pos_search, rows, order = ctx.get_search(n)
+    counts, idx = ctx.get_neighbors(n)
+    assert np.array_equal(pos_search, g["pos_search"])
+    assert np.array_equal(rows, g["rows_sorted"]) and np.array_equal(order, g["order"])
+    assert np.array_equal(counts, g["nbr_count"])
+    flat = np.concatenate([idx[i, :counts[i]] for i in range(n)]) if n_pairs else np.zeros(0, np.int32)
+    assert np.array_equal(flat, g["nbr_idx"])
+    ctx.step_finish(g["noise"])
+    pos, vel, prs = ctx.get_state()
+    assert np.array_equal(prs, g["pressure"])
+    assert np.array_equal(ctx.get_tension(n), g["tension_vec"])
+    assert np.array_equal(vel, g["vel_out"])
+    assert np.array_equal(pos, g["pos_out"])
+
+
+@pytest.mark.parametrize("name", step_goldens())
+def test_step_mixed_reference_noise_within_tolerance(name):
+    g = golden(name)
+    ctx = make_ctx(g, _lib.PRECISION_MIXED, _lib.NOISE_HOST)
+    n, n_pairs = ctx.step_begin()
+    _, rows, order = ctx.get_search(n)
+    counts, _ = ctx.get_neighbors(n)
+    assert np.array_equal(rows, g["rows_sorted"]) and np.array_equal(order, g["order"])  # search is fp64 in both modes
+    assert np.array_equal(counts, g["nbr_count"])
+    ctx.step_finish(g["noise"])
+    pos, vel, prs = ctx.get_state()
+    d = 2 * float(g["coeffs"][1])
+    # the recorded inputs are fp64; mixed mode stores velocities in fp32, so compare against the oracle run on
+    # the fp32-rounded input velocities (what the device actually holds)
+    ref = O.step(g["coeffs"], g["pos_in"], g["vel_in"].astype(np.float32).astype(np.float64), g["segments"],
+                 g["body_len"], g["body_kin"], noise_mode=2, noise=g["noise"])
+    vscale = max(np.abs(ref["vel_out"]).max(), 1.0)
+    assert np.abs(vel - ref["vel_out"]).max() <= REL_TOL_F32 * vscale
+    assert np.abs(pos - ref["pos_out"]).max() <= REL_TOL_F32 * d
+    assert np.abs(prs - ref["pressure"]).max() <= 1e-5 * max(ref["pressure"].max(), 1.0)
+
+
+@pytest.mark.parametrize("name", ["step_stirring_cup_t150.npz", "step_wave_machine_t300.npz"])
+@pytest.mark.parametrize("precision", [_lib.PRECISION_F64, _lib.PRECISION_MIXED])
+def test_step_counter_noise(name, precision):
+    """Production noise: device counter-based uniforms == the oracle's restatement of the same hash."""
+    g = golden(name)
+    ctx = make_ctx(g, precision, _lib.NOISE_COUNTER, seed=1234)
+    ctx.set_tick(77)
+    ctx.step()
+    pos, vel, prs = ctx.get_state()
+    vin = g["vel_in"] if precision == _lib.PRECISION_F64 else g["vel_in"].astype(np.float32).astype(np.float64)
+    ref = O.step(g["coeffs"], g["pos_in"], vin, g["segments"], g["body_len"], g["body_kin"], noise_mode=1,
+                 tkey=O.tick_key(1234, 77))
+    if precision == _lib.PRECISION_F64:
+        assert np.array_equal(prs, ref["pressure"]) and np.array_equal(vel, ref["vel_out"])
+        assert np.array_equal(pos, ref["pos_out"])
+    else:
+        d = 2 * float(g["coeffs"][1])
+        assert np.abs(vel - ref["vel_out"]).max() <= REL_TOL_F32 * max(np.abs(ref["vel_out"]).max(), 1.0)
+        assert np.abs(pos - ref["pos_out"]).max() <= REL_TOL_F32 * d
+
+
+def test_step_no_noise_bit_exact():
+    g = golden("step_wave_machine_t300.npz")
+    ctx = make_ctx(g, _lib.PRECISION_F64, _lib.NOISE_NONE)
+    ctx.step()
+    pos, vel, prs = ctx.get_state()
+    ref = O.step(g["coeffs"], g["pos_in"], g["vel_in"], g["segments"], g["body_len"], g["body_kin"], noise_mode=0)
+    assert np.array_equal(vel, ref["vel_out"]) and np.array_equal(pos, ref["pos_out"])
+    assert np.array_equal(ctx.get_wall_counts(len(pos)), ref["wall_count"])
+
+
+# ---- the drop-in object, whole runs ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40)])
+def test_crate_free_run_bit_exact(name, last):
+    """`Crate(world_config).physics_tick()` x N == the reference's trajectory, bit for bit (fp64 + reference RNG)."""
+    world, g = world_from_freerun(name)
+    crate = Crate(world)
+    for tick in range(1, last + 1):
+        crate.physics_tick()
+        if f"pos_t{tick}" in g.files:
+            assert crate.particle_count == len(g[f"pos_t{tick}"])
+            assert np.array_equal(crate.particles, g[f"pos_t{tick}"]), tick
+            assert np.array_equal(crate.particle_velocities, g[f"vel_t{tick}"]), tick
+            assert np.array_equal(crate.particles_pressure, g[f"pressure_t{tick}"]), tick
+
+
+def test_crate_counter_mode_runs_and_stays_in_box():
+    world, _ = world_from_freerun("wave_machine")
+    crate = Crate(world, precision="mixed", noise="counter")
+    for _ in range(300):
+        crate.physics_tick()
+    pos = crate.particles
+    r = world.coefficients["particle_radius"]
+    assert crate.particle_count > 3000 and np.isfinite(pos).all()
+    assert pos.min() >= -r and pos.max() <= 1 + r
+
+
+# ---- synthetic scenes: GPU vs oracle at sizes the oracle finishes in seconds ------------------------------------
+def _scene_ctx(world, pos, vel, precision, noise_mode, seed=0):
+    c = world.coefficients
+    ctx = _lib.Context(len(pos), precision)
+    ctx.set_params(dt=c["dt"], particle_radius=c["particle_radius"], wall_collision_decay=c["wall_collision_decay"],
+                   pressure_amplifier=c["pressure_amplifier"], ignored_pressure=c["ignored_pressure"],
+                   collider_noise_level=c["collider_noise_level"], viscosity=c["viscosity"],
+                   surface_smoothing=c["surface_smoothing"], target_pressure=c["target_pressure"],
+                   gravity_x=c["gravity"][0], gravity_y=c["gravity"][1])
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    ctx.set_walls(seg, [len(seg)], np.zeros((1, 5)))
+    ctx.set_noise(noise_mode, seed)
+    ctx.set_state(pos, vel)
+    return ctx, seg
+
+
+def _coeff_vec(c):
+    return np.array([c["dt"], c["particle_radius"], c["wall_collision_decay"], c["pressure_amplifier"],
+                     c["ignored_pressure"], c["collider_noise_level"], c["viscosity"], c["surface_smoothing"],
+                     c["target_pressure"], c["gravity"][0], c["gravity"][1]], dtype=np.float64)
+
+
+@pytest.mark.parametrize("maker,n", [(dam_break, 100_000), (box_fill, 60_000)])
+def test_scene_f64_matches_oracle_over_steps(maker, n):
+    """5 consecutive ticks, state NOT re-synchronised: fp64 mode stays bit-identical to the oracle."""
+    world, pos, vel = maker(n)
+    ctx, seg = _scene_ctx(world, pos, vel, _lib.PRECISION_F64, _lib.NOISE_COUNTER, seed=5)
+    cv = _coeff_vec(world.coefficients)
+    rp, rv = pos.copy(), vel.copy()
+    for tick in range(5):
+        ctx.set_tick(tick)
+        ctx.step()
+        out = O.step(cv, rp, rv, seg, [len(seg)], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(5, tick),
+                     want_all=(tick == 4))
+        rp, rv = out["pos_out"], out["vel_out"]
+    gp, gv, gprs = ctx.get_state()
+    assert np.array_equal(gp, rp) and np.array_equal(gv, rv) and np.array_equal(gprs, out["pressure"])
+    counts, idx = ctx.get_neighbors(n)
+    assert np.array_equal(counts, out["nbr_count"]) and np.array_equal(idx, out["nbr_idx_padded"])
+
+
+@pytest.mark.parametrize("maker,n", [(dam_break, 100_000)])
+def test_scene_mixed_per_step_tolerance(maker, n):
+    """Per-step error of the production mode, state re-synchronised from the oracle every step."""
+    world, pos, vel = maker(n)
+    cv = _coeff_vec(world.coefficients)
+    d = 2 * world.coefficients["particle_radius"]
+    # settle a few ticks on the oracle so velocities are non-trivial
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    for tick in range(3):
+        out = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"].astype(np.float32).astype(np.float64)
+    ctx, _ = _scene_ctx(world, pos, vel, _lib.PRECISION_MIXED, _lib.NOISE_COUNTER)
+    ctx.set_tick(3)
+    ctx.step()
+    gp, gv, _ = ctx.get_state()
+    ref = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(0, 3), want_all=False)
+    assert np.abs(gv - ref["vel_out"]).max() <= REL_TOL_F32 * max(np.abs(ref["vel_out"]).max(), 1.0)
+    assert np.abs(gp - ref["pos_out"]).max() <= REL_TOL_F32 * d
+
+
+# ---- size-independent properties at the benchmark size ----------------------------------------------------------
+def test_dam_break_1m_properties():
+    n = 1_000_000
+    world, pos, vel = dam_break(n)
+    ctx, _ = _scene_ctx(world, pos, vel, _lib.PRECISION_MIXED, _lib.NOISE_COUNTER)
+    ctx.step(3)
+    p1, v1, prs = ctx.get_state()
+    assert ctx.particle_count() == n and np.isfinite(p1).all() and np.isfinite(v1).all()
+    r = world.coefficients["particle_radius"]
+    assert p1.min() >= -r and p1.max() <= 1 + r
+    # the sorted order the last search produced really is np.lexsort((x, floor(y / d))) of the search positions
+    ps, rows, order = ctx.get_search(n)
+    d = 2 * r
+    want = np.lexsort((ps[:, 0], np.floor(ps[:, 1] / d).astype(np.int64)))
+    assert np.array_equal(order, want)
+    assert np.array_equal(rows, np.floor(ps[order, 1] / d).astype(np.int64))
+    # neighbor lists: untrimmed lists are symmetric and hold exactly the pairs within one diameter
+    counts, idx = ctx.get_neighbors(n)
+    assert counts.max() <= 20
+    sample = np.random.RandomState(0).choice(n, 2000, replace=False)
+    for i in sample:
+        nb = idx[i, :counts[i]]
+        dist = np.sqrt(((ps[nb] - ps[i]) ** 2).sum(1))
+        assert (dist <= d).all()
+        if counts[i] < 20:
+            for j in nb:
+                if counts[j] < 20:
+                    assert i in idx[j, :counts[j]]
+    # determinism: a second context fed the same inputs produces the same bits
+    ctx2, _ = _scene_ctx(world, pos, vel, _lib.PRECISION_MIXED, _lib.NOISE_COUNTER)
+    ctx2.step(3)
+    p2, v2, _ = ctx2.get_state()
+    assert np.array_equal(p1, p2) and np.array_equal(v1, v2)
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------------
+def test_empty_and_single_particle():
+    g = golden("step_stirring_cup_t150.npz")
+    ctx = _lib.Context(8)
+    ctx.set_params(**params_from_coeffs(g["coeffs"]))
+    ctx.set_walls(g["segments"], g["body_len"], g["body_kin"])
+    ctx.set_noise(_lib.NOISE_NONE)
+    ctx.step()                                   # P = 0
+    assert ctx.particle_count() == 0
+    ctx.set_state(np.array([[0.5, 0.3]]), np.array([[0.1, -0.2]]))
+    ctx.step()
+    pos, vel, prs = ctx.get_state()
+    ref = O.step(g["coeffs"], [[0.5, 0.3]], [[0.1, -0.2]], g["segments"], g["body_len"], g["body_kin"])
+    assert np.array_equal(pos, ref["pos_out"]) and np.array_equal(vel, ref["vel_out"]) and prs[0] == 0
+
+
+def test_removal_append_and_identity():
+    """remove_particles (crate.py:149-159) is stable; appended rows come last; rows keep their identity."""
+    g = golden("step_stirring_cup_t150.npz")
+    pos, vel = g["pos_in"].copy(), g["vel_in"].copy()
+    pos[[3, 50, 200]] = [[-0.2, 0.5], [0.5, 1.2], [1.0051, 0.5]]           # outside [-r, 1 + r]
+    ctx = _lib.Context(1000)
+    ctx.set_params(**params_from_coeffs(g["coeffs"]))
+    ctx.set_walls(g["segments"], g["body_len"], g["body_kin"])
+    ctx.set_noise(_lib.NOISE_COUNTER, 9)
+    ctx.set_state(pos, vel)
+    ctx.step()
+    keep = np.ones(len(pos), bool)
+    keep[[3, 50, 200]] = False
+    uid = np.arange(len(pos), dtype=np.uint32)[keep]
+    ref = O.step(g["coeffs"], pos[keep], vel[keep], g["segments"], g["body_len"], g["body_kin"], noise_mode=1,
+                 tkey=O.tick_key(9, 0), uid=uid)
+    gp, gv, _ = ctx.get_state()
+    assert ctx.particle_count() == keep.sum()
+    assert np.array_equal(ctx.get_uids(), uid)
+    assert np.array_equal(gp, ref["pos_out"]) and np.array_equal(gv, ref["vel_out"])
+    extra = np.array([[0.4, 0.4], [0.41, 0.4]])
+    ctx.append_particles(extra, np.zeros((2, 2)))
+    gp2, _, _ = ctx.get_state()
+    assert np.array_equal(gp2[:-2], gp) and np.array_equal(gp2[-2:], extra)
+    assert ctx.get_uids()[-2:].tolist() == [len(pos), len(pos) + 1]
+
+
+def test_pile_up_in_one_cell_and_trim():
+    """Hundreds of particles in a single cell (in-cell rank sort, 20-trim everywhere), duplicates included."""
+    rs = np.random.RandomState(4)
+    pts = 0.5 + rs.rand(700, 2) * 0.004
+    pts[100:120] = pts[100]                      # exact duplicates: ties broken by original index
+    ctx = _lib.Context(16)
+    rows, order, counts, idx = ctx.detect_particle_collisions(pts, 0.01)
+    r2, o2, c2, i2 = O.detect_particle_collisions(pts, 0.01)
+    assert np.array_equal(order, o2) and np.array_equal(counts, c2) and np.array_equal(idx, i2)
+    assert (counts == 20).all()
+
+
+def test_errors_are_loud():
+    ctx = _lib.Context(4)
+    with pytest.raises(_lib.SandCrateError, match="sc_set_params"):
+        ctx.step()
+    g = golden("step_stirring_cup_t150.npz")
+    ctx.set_params(**params_from_coeffs(g["coeffs"]))
+    with pytest.raises(_lib.SandCrateError, match="capacity"):
+        ctx.set_state(g["pos_in"], g["vel_in"])
+    with pytest.raises(_lib.SandCrateError, match="SC_MAX_SEGMENTS"):
+        ctx.set_walls(np.zeros((40, 4)), [40], np.zeros((1, 5)))
+    ctx.set_noise(_lib.NOISE_HOST)
+    ctx.set_state(g["pos_in"][:4], g["vel_in"][:4])
+    with pytest.raises(_lib.SandCrateError, match="sc_step_begin"):
+        ctx.step()

@@ -1,0 +1,107 @@
+"""CPU tests of the host-side mirror of the reference interface: config schema, rigid bodies, particle sources and
+the `Crate` tick protocol.  The GPU context is replaced by the oracle-backed test double (tests/oracle_backend.py)
+so the whole-run comparison against the reference's recorded trajectories runs without a GPU."""
+import numpy as np
+import pytest
+import yaml
+
+import sand_crate_b200
+from conftest import golden, world_from_freerun
+from oracle_backend import OracleContext
+from sand_crate_b200 import Crate, config_from_dict, crate as crate_mod
+from sand_crate_b200.rigid_body import build_rigid_bodies, rotate_degrees
+from sand_crate_b200.scenes import box_fill, dam_break
+
+
+@pytest.fixture
+def oracle_backend(monkeypatch):
+    monkeypatch.setattr(crate_mod._lib, "Context", OracleContext)
+
+
+def test_config_schema_roundtrip(tmp_path):
+    world, _ = world_from_freerun("stirring_cup")
+    raw = {"playback": {"save_recording": True, "ticks_to_record": 1200, "recording_output_dir_path": "../data",
+                        "screen_x": 1000, "screen_y": 1000},
+           "world": {"coefficients": world.coefficients, "particle_sources": world.particle_sources,
+                     "rigid_bodies": world.rigid_bodies}}
+    path = tmp_path / "cfg.yaml"
+    path.write_text(yaml.safe_dump(raw))
+    cfg = sand_crate_b200.load_config(path)
+    assert cfg.world_config.coefficients == world.coefficients
+    assert cfg.playback_config.ticks_to_record == 1200
+    assert config_from_dict(raw).world_config.rigid_bodies == world.rigid_bodies
+
+
+def test_rotate_degrees_quarter_turns_are_exact():
+    assert rotate_degrees(1.0, 2.0, 90) == (-2.0, 1.0)
+    assert rotate_degrees(1.0, 2.0, -90) == (2.0, -1.0)
+    assert rotate_degrees(1.0, 2.0, 180) == (-1.0, -2.0)
+    x, y = rotate_degrees(1.0, 0.0, -12)
+    assert abs(x - np.cos(np.radians(12))) < 1e-15 and abs(y + np.sin(np.radians(12))) < 1e-15
+
+
+@pytest.mark.parametrize("name", ["stirring_cup", "wave_machine"])
+def test_rigid_bodies_follow_the_reference(name):
+    """Placement (scale -> rotate -> translate) and the linearised motored motion, against recorded segments."""
+    world, g = world_from_freerun(name)
+    bodies = build_rigid_bodies(world.rigid_bodies)
+    dt = world.coefficients["dt"]
+    ticks = [int(t) for t in g["ticks"]]
+    for tick in range(1, max(ticks) + 1):
+        for b in bodies:
+            b.apply_velocity(dt)
+        if tick in ticks:
+            seg = np.vstack([b.segments for b in bodies])
+            assert np.array_equal(seg, g[f"segments_t{tick}"]), tick
+
+
+@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40)])
+def test_crate_protocol_reproduces_reference_trajectory(oracle_backend, name, last):
+    """Sources + RNG protocol + body motion + removal, whole run, bit for bit (step = oracle test double)."""
+    world, g = world_from_freerun(name)
+    crate = Crate(world)
+    for tick in range(1, last + 1):
+        crate.physics_tick()
+        if f"pos_t{tick}" in g.files:
+            assert crate.tick == tick
+            assert crate.particle_count == len(g[f"pos_t{tick}"])
+            assert np.array_equal(crate.particles, g[f"pos_t{tick}"]), tick
+            assert np.array_equal(crate.particle_velocities, g[f"vel_t{tick}"]), tick
+            assert np.array_equal(crate.particles_pressure, g[f"pressure_t{tick}"]), tick
+            assert np.array_equal(crate.segments, g[f"segments_t{tick}"]), tick
+
+
+def test_crate_surface(oracle_backend):
+    world, _ = world_from_freerun("stirring_cup")
+    crate = Crate(world)
+    assert set(crate.editable_coefficients()) == set(world.coefficients)
+    assert crate.diameter == 2 * world.coefficients["particle_radius"]
+    assert crate.segments.shape == (6, 2, 2) and crate.particle_count == 0 and crate.tick == 0
+    crate.viscosity = crate.viscosity * 1.1            # live edit, playback.py:221-226
+    crate.gravity = np.array([0.0, -9.81])              # playback.py:151-153
+    crate.physics_tick()
+    assert crate._ctx.params["viscosity"] == pytest.approx(8.8) and crate._ctx.params["gravity_y"] == -9.81
+    assert "Tick: 1" in crate.debug_prints and "viscosity" in crate.debug_prints
+    assert crate.debug_arrows == []
+
+
+def test_crate_grows_capacity(oracle_backend):
+    world, _ = world_from_freerun("stirring_cup")
+    crate = Crate(world, capacity=8)
+    for _ in range(6):
+        crate.physics_tick()
+    assert crate.particle_count > 8 and crate._ctx.capacity >= crate.particle_count
+
+
+@pytest.mark.parametrize("maker,n", [(dam_break, 20000), (box_fill, 10000)])
+def test_synthetic_scenes(maker, n):
+    world, pos, vel = maker(n)
+    c = world.coefficients
+    d = 2 * c["particle_radius"]
+    assert pos.shape == (n, 2) and vel.shape == (n, 2) and not vel.any()
+    assert pos.min() > 0.5 * d and pos.max() < 1 - 0.5 * d                 # inside the box, off the walls
+    assert c["dt"] == pytest.approx(0.002 * d / 0.01) and c["max_particles"] == n
+    # lattice spacing 0.75 d: about 1.8 particles per d x d cell where the liquid is
+    cells = np.floor(pos / d).astype(np.int64)
+    occ = np.unique(cells[:, 0] * 100000 + cells[:, 1], return_counts=True)[1]
+    assert 1.5 < occ.mean() < 2.1
