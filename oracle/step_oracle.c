@@ -348,6 +348,7 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
     int32_t *counts = (int32_t *)malloc(sizeof(int32_t) * (size_t)P);
     int32_t *idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)P * OC_MAX_NEIGHBORS);
     if (!counts || !idx) return -1;
+    memset(idx, 0xFF, sizeof(int32_t) * (size_t)P * OC_MAX_NEIGHBORS); /* -1 padding */
     if (oc_detect_particle_collisions(pos, P, d, NULL, NULL, counts, idx)) return -1;
     if (counts_out) memcpy(counts_out, counts, sizeof(int32_t) * (size_t)P);
     if (idx_out) memcpy(idx_out, idx, sizeof(int32_t) * (size_t)P * OC_MAX_NEIGHBORS);
