@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py - particle-steps/sec of the SandCrate step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--scene dam_break|box_fill]
+    python bench.py --impl reference ...        # the CPU port of the reference step on the host cores
+
+One "step" = one `physics_tick` over the whole synthetic scene.  N = 1: dam-break, 1M particles (BASELINE.json
+configs[2]).  Timed with CUDA events on the stream the kernels are launched on; L2 is flushed between timed steps
+(the 1M scene's working set is smaller than the 126 MB L2).  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_sec"
+UNIT = "particle-steps/s"
+# algorithmic bytes per particle per launch, mixed layout
+ALGO_BYTES = {"prepass_wall_key": 20 + 4, "place": 12, "rank_gather": 4 + 28 + 32, "density": 16 + 4 + 4 + 12,
+              "force_integrate": 60}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def scene_params(world):
+    c = world.coefficients
+    return dict(dt=c["dt"], particle_radius=c["particle_radius"], wall_collision_decay=c["wall_collision_decay"],
+                pressure_amplifier=c["pressure_amplifier"], ignored_pressure=c["ignored_pressure"],
+                collider_noise_level=c["collider_noise_level"], viscosity=c["viscosity"],
+                surface_smoothing=c["surface_smoothing"], target_pressure=c["target_pressure"],
+                gravity_x=c["gravity"][0], gravity_y=c["gravity"][1])
+
+
+def coeff_vec(world):
+    p = scene_params(world)
+    return np.array([p[k] for k in ("dt", "particle_radius", "wall_collision_decay", "pressure_amplifier",
+                                    "ignored_pressure", "collider_noise_level", "viscosity", "surface_smoothing",
+                                    "target_pressure", "gravity_x", "gravity_y")])
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9 or not f[1].isdigit():
+                    continue
+                sm.append(int(f[1]))
+                out["sm_max_mhz"] = int(f[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def run_reference_arm(a):
+    """The reference's CPU implementation of the path on this box's host cores.  The reference itself is pure
+    Python and cannot travel to the GPU box, so this is the oracle port (oracle/step_oracle.c; OpenMP over
+    particles for the force loops, scalar neighbor search), on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from sand_crate_b200.scenes import SCENES
+    n = a.cpu_particles
+    world, pos, vel = SCENES[a.scene](n)
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = coeff_vec(world)
+    kin = np.zeros((1, 5))
+    tick = 0
+    for _ in range(a.warmup):
+        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+        tick += 1
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+        tick += 1
+    dt = time.perf_counter() - t0
+    value = n * a.steps / dt
+    cores = O.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{a.scene} {a.particles} particles (CPU sample: {n} particles)", "scene": a.scene,
+                   "particles": a.particles},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{a.scene} {n} particles x {a.steps} ticks, oracle/step_oracle.c, {cores} OpenMP threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(scene, budget_s=15.0):
+    """cpu_baseline leg: the oracle port on a bounded sample (about budget_s of CPU work)."""
+    from oracle import oracle as O
+    from sand_crate_b200.scenes import SCENES
+    n = 200_000
+    world, pos, vel = SCENES[scene](n)
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = coeff_vec(world)
+    kin = np.zeros((1, 5))
+    out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, 0), want_all=False)  # warm
+    pos, vel = out["pos_out"], out["vel_out"]
+    t0 = time.perf_counter()
+    ticks = 0
+    while True:
+        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, 1 + ticks), want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+        ticks += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or ticks >= 200:
+            break
+    cores = O.num_threads()
+    return {"value": n * ticks / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{scene} {n} particles x {ticks} ticks in {el:.1f}s, oracle/step_oracle.c, {cores} OpenMP threads "
+                      f"(neighbor search scalar)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="dam_break", choices=["dam_break", "box_fill"])
+    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
+    ap.add_argument("--cpu-particles", type=int, default=200_000)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        if a.steps == 200 and a.warmup == 100:  # defaults sized for the GPU arm; keep the CPU arm to ~a minute
+            a.steps, a.warmup = 20, 3
+        a.warmup = max(a.warmup, 1)
+        return run_reference_arm(a)
+    a.warmup = max(a.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from sand_crate_b200 import Crate, _lib
+    from sand_crate_b200.scenes import SCENES
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = a.particles
+    world, pos, vel = SCENES[a.scene](n, seed=42 + rank)
+    # a non-default torch stream: the library launches on it and torch.cuda.Event records on it (handle 0, the
+    # legacy default stream, would make sc_create open a private stream that torch events cannot see)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    precision = _lib.PRECISION_MIXED if a.precision == "mixed" else _lib.PRECISION_F64
+    ctx = _lib.Context(n, precision, local_rank, stream)
+    ctx.set_params(**scene_params(world))
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    ctx.set_walls(seg, [4], np.zeros((1, 5)))
+    ctx.set_noise(_lib.NOISE_COUNTER, 0)
+    ctx.set_state(pos, vel)
+
+    flush = None if a.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ctx.step(a.warmup)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for e0, e1 in ev:
+        if flush is not None:
+            flush.fill_(1)          # untimed: evicts the previous step's lines from the 126 MB L2
+        e0.record()
+        ctx.step()
+        e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
+    total_ms = float(step_ms.sum())
+    kernels = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
+    n_live = ctx.particle_count()
+
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world_size * n * a.steps / (total_ms_max * 1e-3)
+
+    # ---- e2e: the public API with host buffers: upload state, tick, read the result back, every step ----------
+    crate = Crate(world, precision=a.precision, noise="counter", device=local_rank, capacity=n, stream=stream)
+    hp = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
+    hv = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
+    gp, gv, _ = ctx.get_state(want_pressure=False)
+    hp[:], hv[:] = gp, gv
+    for _ in range(3):
+        crate.set_particles(hp, hv)
+        crate.physics_tick()
+        _ = crate.particles
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        crate.set_particles(hp, hv)
+        crate.physics_tick()
+        out_pos = crate._ctx.get_state(want_vel=False, want_pressure=False)[0]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world_size * n * a.e2e_steps / float(t.item())
+    assert np.isfinite(out_pos).all()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        dom = "force_integrate"
+        k = kernels.get(dom, {"launches": 1, "ms": float("nan")})
+        k_ms = k["ms"] / max(k["launches"], 1)
+        achieved = ALGO_BYTES[dom] * n / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)
+        per_kernel = {}
+        for name, v in kernels.items():
+            ms = v["ms"] / max(v["launches"], 1)
+            per_kernel[name] = {"ms": round(ms, 5), "launches_per_step": round(v["launches"] / a.steps, 2)}
+            if name in ALGO_BYTES:
+                per_kernel[name]["algo_gbs"] = round(ALGO_BYTES[name] * n / (ms * 1e-3) / 1e9, 1)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 forces / f64 positions" if a.precision == "mixed" else "f64", "data": "synthetic",
+            "config": {"workload": f"{a.scene} {n} particles per GPU, closed unit box, counter noise 0.1",
+                       "scene": a.scene, "particles_per_gpu": n, "live_particles_rank0": n_live,
+                       "parallelism": "single GPU" if world_size == 1 else f"{world_size} independent replicas",
+                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes),
+                    "d2h_bytes_per_step": int(out_pos.nbytes), "steps": a.e2e_steps,
+                    "api": "Crate.set_particles(host) -> physics_tick() -> particles (host)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle": ALGO_BYTES[dom], "kernel_ms": k_ms},
+            "kernels": per_kernel,
+            "wall_s_timed_region": wall,
+        }
+        if not a.no_cpu_baseline and world_size == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(a.scene)
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

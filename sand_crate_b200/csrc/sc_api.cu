@@ -157,6 +157,8 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
     return 0;
 }
 
+static void refresh_wall_boxes(sc_ctx *ctx);
+
 static int refresh_dev_params(sc_ctx *ctx) {
     const sc_params &h = ctx->hp;
     DevParams &p = ctx->dp;
@@ -247,7 +249,10 @@ extern "C" int sc_set_params(sc_ctx *ctx, const sc_params *p) {
         const int lo = (int)std::floor((-2 * r) / d) - 1, hi = (int)std::floor((1 + 2 * r) / d) + 1;
         CKR(setup_grid(ctx, d, lo, hi, lo, hi));
         ctx->srt_valid = false;
-        if (ctx->walls_set) sc_pad_segments(&ctx->walls.seg[0][0], ctx->walls.S, r, &ctx->walls.pad[0][0]);
+        if (ctx->walls_set) {
+            sc_pad_segments(&ctx->walls.seg[0][0], ctx->walls.S, r, &ctx->walls.pad[0][0]);
+            refresh_wall_boxes(ctx);
+        }
     }
     ctx->params_set = true;
     return 0;
@@ -266,6 +271,20 @@ extern "C" int sc_pad_segments(const double *segments, int S, double pad, double
         p2[0] = bx - ox; p2[1] = by - oy; p2[2] = ax - ox; p2[3] = ay - oy;
     }
     return 0;
+}
+
+// bounding boxes for the conservative culls of WallParams (grown so that rounding can never cull a true hit)
+static void refresh_wall_boxes(sc_ctx *ctx) {
+    WallParams &w = ctx->walls;
+    auto grow = [](double *box, double ax, double ay, double bx, double by, double m) {
+        const double xmin = std::fmin(ax, bx), xmax = std::fmax(ax, bx), ymin = std::fmin(ay, by), ymax = std::fmax(ay, by);
+        const double scale = std::fmax(1.0, std::fmax(std::fmax(std::fabs(xmin), std::fabs(xmax)),
+                                                      std::fmax(std::fabs(ymin), std::fabs(ymax))));
+        const double e = m * (1.0 + 1e-6) + 1e-12 * scale;
+        box[0] = xmin - e; box[1] = xmax + e; box[2] = ymin - e; box[3] = ymax + e;
+    };
+    for (int k = 0; k < w.S; ++k) grow(w.seg_box[k], w.seg[k][0], w.seg[k][1], w.seg[k][2], w.seg[k][3], ctx->dp.touch);
+    for (int k = 0; k < 2 * w.S; ++k) grow(w.pad_box[k], w.pad[k][0], w.pad[k][1], w.pad[k][2], w.pad[k][3], 0.0);
 }
 
 extern "C" int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const int32_t *body_len,
@@ -287,6 +306,7 @@ extern "C" int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const in
     if (k != S) return fail(ctx, "sc_set_walls: body_len does not sum to S");
     if (S) std::memcpy(&w.seg[0][0], segments, sizeof(double) * 4 * (size_t)S);
     sc_pad_segments(&w.seg[0][0], S, ctx->dp.r, &w.pad[0][0]);
+    refresh_wall_boxes(ctx);
     ctx->walls_set = true;
     return 0;
 }

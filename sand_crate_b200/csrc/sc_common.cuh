@@ -42,6 +42,11 @@ struct WallParams {
     double pad[2 * SC_MAX_SEGMENTS][4];   // pad_segments(segments, r)            (geometry_utils.py:146-172)
     int seg_body[SC_MAX_SEGMENTS];
     double kin[SC_MAX_BODIES][5];         // vcx, vcy, omega, posx, posy          (rigid_body.py:18-34)
+    // conservative culls (never change a result, only skip work): a wall contact needs the particle inside the
+    // segment's bounding box grown by the touch distance; a crossing needs the movement's box to meet the padded
+    // segment's box.  (xmin, xmax, ymin, ymax), grown by a few ulps on the host.
+    double seg_box[SC_MAX_SEGMENTS][4];
+    double pad_box[2 * SC_MAX_SEGMENTS][4];
 };
 
 // device-resident counters, zeroed/updated on the stream (no host round trip in the step)

@@ -21,14 +21,41 @@ template <> struct Vec2<float> { typedef float2 type; };
 __device__ inline double sc_sqrt(double v) { return sqrt(v); }
 __device__ inline float sc_sqrt(float v) { return sqrtf(v); }
 
-// Visits the neighbors of sorted particle s in reference order.  f(j, pj) is called for each accepted j.
-// Acceptance is evaluated in fp64 in both precision modes: the x-window from the LOWER-sorted particle
-// (collision_detector.py:106-119) and sqrt(dx*dx + dy*dy) <= d (collision_detector.py:77-79).
-template <class F>
-__device__ __forceinline__ int for_each_neighbor(uint32_t s, double2 ps, uint32_t c, const Grid &g,
+// Per-thread neighbor list kept in shared memory, one column per thread (conflict-free: slot k of thread t is
+// word k * SC_BLOCK + t).
+struct NbrList {
+    uint32_t *col;
+    __device__ __forceinline__ uint32_t get(int k) const { return col[k * SC_BLOCK]; }
+    __device__ __forceinline__ void set(int k, uint32_t j) { col[k * SC_BLOCK] = j; }
+};
+
+// The reference accepts a pair iff sqrt(dx*dx + dy*dy) <= d in fp64 (collision_detector.py:77-79).  q = dx*dx+dy*dy
+// is formed exactly as NumPy forms it; sqrt is correctly rounded and monotone, so outside a 2^-40 relative band
+// around d*d the outcome is decided by q alone and the fp64 sqrt (about 30 instructions) is only evaluated inside
+// the band - bit-identical decisions, including the lattice cases that sit exactly on q == d*d.
+struct AcceptBand {
+    double d, d2_lo, d2_hi;
+    __device__ __forceinline__ explicit AcceptBand(double d_) : d(d_) {
+        const double d2 = d_ * d_;
+        d2_lo = d2 * (1.0 - 9.094947017729282e-13);  // 2^-40
+        d2_hi = d2 * (1.0 + 9.094947017729282e-13);
+    }
+    __device__ __forceinline__ bool operator()(double dx, double dy) const {
+        const double q = dx * dx + dy * dy;
+        if (q > d2_hi) return false;
+        if (q < d2_lo) return true;
+        return sqrt(q) <= d;  // also where NaN ends up: false, like the reference
+    }
+};
+
+// Phase 1 of both pair kernels: collects the neighbors of sorted particle s in EXACTLY the reference's list order
+// into `lst` and returns their number (<= 20).  Acceptance is evaluated in fp64 in both precision modes: the
+// x-window from the LOWER-sorted particle (collision_detector.py:106-119) and the distance test above.
+__device__ __forceinline__ int collect_neighbors(uint32_t s, double2 ps, uint32_t c, const Grid &g,
                                                  const uint32_t *__restrict__ cell_start,
-                                                 const double2 *__restrict__ pos, F &&f) {
+                                                 const double2 *__restrict__ pos, NbrList lst) {
     const double d = g.d;
+    const AcceptBand accept(d);
     int count = 0;
     const uint32_t a1 = cell_start[c + 2];
     const uint32_t cn = c + (uint32_t)g.ncols, cp = c - (uint32_t)g.ncols;
@@ -37,8 +64,7 @@ __device__ __forceinline__ int for_each_neighbor(uint32_t s, double2 ps, uint32_
     for (uint32_t j = s + 1; j < a1 && count < SC_MAX_NEIGHBORS; ++j) {
         const double2 pj = pos[j];
         if (!(pj.x <= xs_hi)) break;  // sorted by x inside the row: nothing further can pass the window
-        const double dx = pj.x - ps.x, dy = pj.y - ps.y;
-        if (sqrt(dx * dx + dy * dy) <= d) { f(j, pj); ++count; }
+        if (accept(pj.x - ps.x, pj.y - ps.y)) lst.set(count++, j);
     }
     // next row, ascending
     {
@@ -46,8 +72,7 @@ __device__ __forceinline__ int for_each_neighbor(uint32_t s, double2 ps, uint32_
         for (uint32_t j = b0; j < b1 && count < SC_MAX_NEIGHBORS; ++j) {
             const double2 pj = pos[j];
             if (!(xs_lo <= pj.x && pj.x <= xs_hi)) continue;
-            const double dx = pj.x - ps.x, dy = pj.y - ps.y;
-            if (sqrt(dx * dx + dy * dy) <= d) { f(j, pj); ++count; }
+            if (accept(pj.x - ps.x, pj.y - ps.y)) lst.set(count++, j);
         }
     }
     // same row, descending from s - 1: j is the lower-sorted one, so the window is evaluated from j
@@ -57,8 +82,7 @@ __device__ __forceinline__ int for_each_neighbor(uint32_t s, double2 ps, uint32_
             --j;
             const double2 pj = pos[j];
             if (!(ps.x <= pj.x + d)) break;
-            const double dx = ps.x - pj.x, dy = ps.y - pj.y;
-            if (sqrt(dx * dx + dy * dy) <= d) { f(j, pj); ++count; }
+            if (accept(ps.x - pj.x, ps.y - pj.y)) lst.set(count++, j);
         }
     }
     // previous row, descending
@@ -68,8 +92,7 @@ __device__ __forceinline__ int for_each_neighbor(uint32_t s, double2 ps, uint32_
             --j;
             const double2 pj = pos[j];
             if (!(pj.x - d <= ps.x && ps.x <= pj.x + d)) continue;
-            const double dx = ps.x - pj.x, dy = ps.y - pj.y;
-            if (sqrt(dx * dx + dy * dy) <= d) { f(j, pj); ++count; }
+            if (accept(ps.x - pj.x, ps.y - pj.y)) lst.set(count++, j);
         }
     }
     return count;
@@ -189,18 +212,20 @@ k_density(const Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t 
     const double2 ps = pos[s];
     const uint32_t uid_s = uid[s];
     const uint32_t nbase = (P.noise_mode == SC_NOISE_HOST) ? noise_off[rank_of_uid[uid_s]] : 0u;
+    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
+    NbrList lst{s_list + threadIdx.x};
+    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
     Real ax = 0, ay = 0;
-    int k = 0;
     Real psum = 0;
     double wl[sizeof(Real) == 8 ? SC_MAX_NEIGHBORS : 1];  // fp64 only: np.sum's pairwise order needs the list
-    const int K = for_each_neighbor(s, ps, cell_key[s], g, cell_start, pos, [&](uint32_t j, double2 pj) {
-        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pj, uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+    for (int k = 0; k < K; ++k) {
+        const uint32_t j = lst.get(k);
+        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
         if constexpr (sizeof(Real) == 8) wl[k] = (double)pg.w; else psum += pg.w;
         const Real c = (1 - pg.w) * pg.w;
         const Real tx = c * pg.nx, ty = c * pg.ny;
         if (k == 0) { ax = tx; ay = ty; } else { ax += tx; ay += ty; }
-        ++k;
-    });
+    }
     Real p = 0;
     if (K > 0) {
         Real pr;
@@ -242,10 +267,12 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
     Real tx = 0, ty = 0;  // F3 sum
     Real qx = 0, qy = 0;  // F5 sum
     Real sum_vx = 0, sum_vy = 0;         // fp32 mode: sum of neighbor velocities
-    uint32_t nbr[sizeof(Real) == 8 ? SC_MAX_NEIGHBORS : 1];  // fp64 mode: list kept for the exact F6 pass
-    int k = 0;
-    const int K = for_each_neighbor(s, ps, cell_key[s], g, cell_start, pos, [&](uint32_t j, double2 pj) {
-        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pj, uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
+    NbrList lst{s_list + threadIdx.x};
+    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
+    for (int k = 0; k < K; ++k) {
+        const uint32_t j = lst.get(k);
+        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
         const Real p_j = pressure[j];
         const R2 s_j = tension[j];
         // F3 pass 2, crate.py:347-353
@@ -258,10 +285,8 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
         const Real ps_ = p_i + p_j;
         const Real fx = pg.nx * ps_, fy = pg.ny * ps_;
         if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; } else { tx += ex; ty += ey; qx += fx; qy += fy; }
-        if constexpr (sizeof(Real) == 8) nbr[k] = j;
-        else { const R2 vj = vel[j]; sum_vx += vj.x; sum_vy += vj.y; }
-        ++k;
-    });
+        if constexpr (sizeof(Real) == 4) { const R2 vj = vel[j]; sum_vx += vj.x; sum_vy += vj.y; }
+    }
 
     // walls: contacts are recomputed from the position the particle had BEFORE apply_hard_wall_fix
     // (crate.py:216 runs before 202-211 and the vectors are never refreshed)
@@ -310,7 +335,7 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
         Real ax = 0, ay = 0;
         if constexpr (sizeof(Real) == 8) {
             for (int q = 0; q < K; ++q) {
-                const R2 vj = vel[nbr[q]];
+                const R2 vj = vel[lst.get(q)];
                 const Real ex = vj.x - vx, ey = vj.y - vy;
                 if (q == 0) { ax = ex; ay = ey; } else { ax += ex; ay += ey; }
             }
@@ -340,7 +365,10 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
         const double bx = ps.x + mvx, by = ps.y + mvy;
         const double bax = bx - ps.x, bay = by - ps.y;
         double f = 1.0;
+        const double mxlo = fmin(ps.x, bx), mxhi = fmax(ps.x, bx), mylo = fmin(ps.y, by), myhi = fmax(ps.y, by);
         for (int q = 0; q < 2 * W.S; ++q) {
+            if (mxhi < W.pad_box[q][0] || mxlo > W.pad_box[q][1] || myhi < W.pad_box[q][2] || mylo > W.pad_box[q][3])
+                continue;  // the movement cannot reach this padded segment
             const double cx = W.pad[q][0], cy = W.pad[q][1], ex = W.pad[q][2], ey = W.pad[q][3];
             const double cdx = ex - cx, cdy = ey - cy;
             const bool opposite = (cdy * bax + (-cdx) * bay) < 0;        // geometry_utils.py:205

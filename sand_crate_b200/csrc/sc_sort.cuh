@@ -32,6 +32,8 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
         int V = 0;
         double sx = 0, sy = 0;
         for (int q = 0; q < W.S; ++q) {
+            if (p.x < W.seg_box[q][0] || p.x > W.seg_box[q][1] || p.y < W.seg_box[q][2] || p.y > W.seg_box[q][3])
+                continue;  // cannot be within the touch distance of this segment
             double cx, cy;
             const double dist = point_segment(p.x, p.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy);
             if (dist <= P.touch) {
@@ -212,11 +214,11 @@ k_count_neighbors(Counters *__restrict__ cnt, Grid g, const uint32_t *__restrict
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const double2 ps = pos[s];
-    int k = 0;
-    const int K = for_each_neighbor(s, ps, cell_key[s], g, cell_start, pos, [&](uint32_t j, double2) {
-        if (list_sorted) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = j;
-        ++k;
-    });
+    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
+    NbrList lst{s_list + threadIdx.x};
+    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
+    if (list_sorted)
+        for (int k = 0; k < K; ++k) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = lst.get(k);
     count_by_rank[rank_of_uid[uid[s]]] = (uint32_t)K;
     atomicAdd(&cnt->n_pairs, (uint32_t)K);
 }
