@@ -45,6 +45,8 @@ struct sc_ctx {
     uint32_t *cell_start = nullptr; size_t cell_cap = 0;
     uint32_t *bsum = nullptr; size_t bsum_cap = 0;
     void *pressure = nullptr, *tension = nullptr;
+    void *pairs = nullptr;            // PairRec<Real>[cap * SC_MAX_NEIGHBORS], written by K4, read by K5
+    uint32_t *pair_off = nullptr; uint8_t *pair_cnt = nullptr;
     uint32_t *wall_bits_cur = nullptr, *wall_bits_srt = nullptr, *wall_slot_cur = nullptr, *wall_slot_srt = nullptr;
     double2 *wall_pre = nullptr;
     Counters *cnt = nullptr;
@@ -207,6 +209,8 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
     rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
     rc |= dev_alloc(c, (char **)&c->pressure, n * rs); rc |= dev_alloc(c, (char **)&c->tension, n * 2 * rs);
+    rc |= dev_alloc(c, (char **)&c->pairs, n * SC_MAX_NEIGHBORS * (rs == 8 ? 32 : 16));
+    rc |= dev_alloc(c, &c->pair_off, n); rc |= dev_alloc(c, &c->pair_cnt, n);
     rc |= dev_alloc(c, &c->wall_bits_cur, n / 32 + 1); rc |= dev_alloc(c, &c->wall_bits_srt, n / 32 + 1);
     rc |= dev_alloc(c, &c->wall_slot_cur, n); rc |= dev_alloc(c, &c->wall_slot_srt, n);
     rc |= dev_alloc(c, &c->wall_pre, n);
@@ -225,7 +229,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->pressure, c->tension,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->pressure, c->tension, c->pairs, c->pair_off, c->pair_cnt,
                     c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -285,6 +289,32 @@ static void refresh_wall_boxes(sc_ctx *ctx) {
     };
     for (int k = 0; k < w.S; ++k) grow(w.seg_box[k], w.seg[k][0], w.seg[k][1], w.seg[k][2], w.seg[k][3], ctx->dp.touch);
     for (int k = 0; k < 2 * w.S; ++k) grow(w.pad_box[k], w.pad[k][0], w.pad[k][1], w.pad[k][2], w.pad[k][3], 0.0);
+    // Largest-area-greedy rectangle inside the world box that meets none of the boxes.  Only ever used as
+    // "strictly inside -> nothing to test", so any rectangle that meets no box is correct; greedy just makes it big.
+    auto safe_rect = [&](double (*boxes)[4], int nb, double *out) {
+        double r[4] = {ctx->dp.box_lo, ctx->dp.box_hi, ctx->dp.box_lo, ctx->dp.box_hi};
+        auto meets = [&](const double *b) { return b[0] < r[1] && b[1] > r[0] && b[2] < r[3] && b[3] > r[2]; };
+        for (int pass = 0; pass < nb + 1; ++pass) {
+            bool changed = false;
+            for (int k = 0; k < nb; ++k) {
+                const double *b = boxes[k];
+                if (!meets(b)) continue;
+                const double w_ = r[1] - r[0], h_ = r[3] - r[2];
+                const double area[4] = {(r[1] - b[1]) * h_, (b[0] - r[0]) * h_, w_ * (r[3] - b[3]), w_ * (b[2] - r[2])};
+                int best = 0;
+                for (int q = 1; q < 4; ++q) if (area[q] > area[best]) best = q;
+                if (best == 0) r[0] = b[1]; else if (best == 1) r[1] = b[0]; else if (best == 2) r[2] = b[3]; else r[3] = b[2];
+                changed = true;
+            }
+            if (!changed) break;
+        }
+        bool ok = r[0] < r[1] && r[2] < r[3];
+        for (int k = 0; ok && k < nb; ++k) ok = !meets(boxes[k]);
+        if (!ok) { r[0] = 1; r[1] = 0; r[2] = 1; r[3] = 0; }  // empty: nothing is skipped
+        for (int q = 0; q < 4; ++q) out[q] = r[q];
+    };
+    safe_rect(w.seg_box, w.S, w.safe_contact);
+    safe_rect(w.pad_box, 2 * w.S, w.safe_ccd);
 }
 
 extern "C" int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const int32_t *body_len,
@@ -513,33 +543,36 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
     dp.noise_mode = (ctx->noise_mode != SC_NOISE_NONE && ctx->hp.collider_noise_level == 0.0) ? SC_NOISE_NONE
                                                                                              : ctx->noise_mode;
     dp.tick_key = tick_key(ctx->seed, ctx->tick);
+    const uint32_t *n_ptr = ctx->cell_start + g.ncells;
     if (n > 0) {
         if (ctx->precision == SC_PRECISION_F64) {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 k_density<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
                     ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
-                    noise_off, ctx->rank_of_uid, (double *)ctx->pressure, (double2 *)ctx->tension);
+                    noise_off, ctx->rank_of_uid, (PairRec<double> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt,
+                    (double *)ctx->pressure, (double2 *)ctx->tension);
             }
             ProfScope ps(ctx, SLOT_FORCE);
             k_force<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, g, dp, ctx->walls, ctx->cell_start, ctx->pos_srt, (const double2 *)ctx->vel_srt,
-                ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev, noise_off, ctx->rank_of_uid,
-                (const double *)ctx->pressure, (const double2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt,
-                ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur);
+                n_ptr, dp, ctx->walls, ctx->pos_srt, (const double2 *)ctx->vel_srt,
+                (const PairRec<double> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt, (const double *)ctx->pressure,
+                (const double2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
+                (double2 *)ctx->vel_cur);
         } else {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 k_density<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
                     ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
-                    noise_off, ctx->rank_of_uid, (float *)ctx->pressure, (float2 *)ctx->tension);
+                    noise_off, ctx->rank_of_uid, (PairRec<float> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt,
+                    (float *)ctx->pressure, (float2 *)ctx->tension);
             }
             ProfScope ps(ctx, SLOT_FORCE);
             k_force<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, g, dp, ctx->walls, ctx->cell_start, ctx->pos_srt, (const float2 *)ctx->vel_srt,
-                ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev, noise_off, ctx->rank_of_uid,
-                (const float *)ctx->pressure, (const float2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt,
-                ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur);
+                n_ptr, dp, ctx->walls, ctx->pos_srt, (const float2 *)ctx->vel_srt,
+                (const PairRec<float> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt, (const float *)ctx->pressure,
+                (const float2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
+                (float2 *)ctx->vel_cur);
         }
     }
     {

@@ -47,6 +47,10 @@ struct WallParams {
     // segment's box.  (xmin, xmax, ymin, ymax), grown by a few ulps on the host.
     double seg_box[SC_MAX_SEGMENTS][4];
     double pad_box[2 * SC_MAX_SEGMENTS][4];
+    // one rectangle (x0, x1, y0, y1; empty when x0 > x1) that no seg_box / no pad_box meets: the single test
+    // that lets the bulk of the liquid skip the per-segment loops altogether
+    double safe_contact[4];
+    double safe_ccd[4];
 };
 
 // device-resident counters, zeroed/updated on the stream (no host round trip in the step)
@@ -56,7 +60,8 @@ struct Counters {
     uint32_t n_wall;     // particles touching a wall this tick
     uint32_t n_pairs;    // sum K_i (filled by the count kernel)
     uint32_t overflow;   // capacity problems seen on the device
-    uint32_t pad_[3];
+    uint32_t pair_cursor;  // next free record of the pair buffer (bump allocator, reset every tick)
+    uint32_t pad_[2];
 };
 
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
@@ -115,5 +120,33 @@ __device__ inline uint32_t cell_of(const Grid &g, double x, double y, int &row_o
 // total order used inside a cell: x ascending (NaN last, like np.lexsort), ties by uid (lexsort is stable and
 // original index order == uid order)
 __device__ inline bool x_less(double a, double b) { return a < b || (b != b && a == a); }
+
+// exclusive prefix sum over the SC_BLOCK threads of a block; `total` = sum over the block
+__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
+    __shared__ uint32_t warp_sums[SC_BLOCK / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < SC_BLOCK / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < SC_BLOCK / 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < SC_BLOCK / 32) warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    total = warp_sums[SC_BLOCK / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
 
 }  // namespace sc

@@ -44,8 +44,10 @@ struct AcceptBand {
         const double q = dx * dx + dy * dy;
         if (q > d2_hi) return false;
         if (q < d2_lo) return true;
-        return sqrt(q) <= d;  // also where NaN ends up: false, like the reference
+        return in_band(q, d);  // also where NaN ends up: false, like the reference
     }
+    // out of line on purpose: inlined, ptxas hoists the fp64 sqrt sequence in front of the two fast exits
+    static __device__ __noinline__ bool in_band(double q, double d) { return sqrt(q) <= d; }
 };
 
 // Phase 1 of both pair kernels: collects the neighbors of sorted particle s in EXACTLY the reference's list order
@@ -197,30 +199,56 @@ __device__ inline double np_sum_1d(const double *a, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K4: pressure p_i and surface normal s_i
+// One record per directed pair (i <- j), produced by K4 and consumed by K5, so the pair geometry - including the
+// noise hash and the reciprocal square root - is evaluated once per tick instead of twice.  HBM is the idle
+// resource on this path (the kernels are issue-bound), so 16 bytes per pair are a good trade.
+template <typename Real> struct PairRec;
+template <> struct __align__(16) PairRec<float> { uint32_t j; float nx, ny, w; };
+template <> struct __align__(16) PairRec<double> { double nx, ny, w; uint32_t j, pad_; };
+
+// K4: neighbor discovery, pair geometry, pressure p_i and surface normal s_i
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_density(const Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
+k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
           const double2 *__restrict__ pos, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ uid,
           const double *__restrict__ host_noise, const uint32_t *__restrict__ noise_off,
-          const uint32_t *__restrict__ rank_of_uid, Real *__restrict__ pressure,
+          const uint32_t *__restrict__ rank_of_uid, PairRec<Real> *__restrict__ pairs,
+          uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, Real *__restrict__ pressure,
           typename Vec2<Real>::type *__restrict__ tension) {
+    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
+    __shared__ uint32_t s_base;
     const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    (void)cnt;
-    const double2 ps = pos[s];
+    const bool live = s < n;
+    NbrList lst{s_list + threadIdx.x};
+    double2 ps = make_double2(0, 0);
+    int K = 0;
+    if (live) {
+        ps = pos[s];
+        K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
+    }
+    // the block's records go to one contiguous chunk of the pair buffer (one atomic per block; where the chunk
+    // lands is arbitrary, but it is only ever reached through pair_off, so results do not depend on it)
+    uint32_t total;
+    const uint32_t before = block_exclusive_scan((uint32_t)K, total);
+    if (threadIdx.x == 0) s_base = total ? atomicAdd(&cnt->pair_cursor, total) : 0u;
+    __syncthreads();
+    if (!live) return;
+    const uint32_t off = s_base + before;
+    pair_off[s] = off;
+    pair_cnt[s] = (uint8_t)K;
     const uint32_t uid_s = uid[s];
     const uint32_t nbase = (P.noise_mode == SC_NOISE_HOST) ? noise_off[rank_of_uid[uid_s]] : 0u;
-    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
-    NbrList lst{s_list + threadIdx.x};
-    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
     Real ax = 0, ay = 0;
     Real psum = 0;
     double wl[sizeof(Real) == 8 ? SC_MAX_NEIGHBORS : 1];  // fp64 only: np.sum's pairwise order needs the list
     for (int k = 0; k < K; ++k) {
         const uint32_t j = lst.get(k);
         const PairGeom<Real> pg = pair_geom<Real>(P, ps, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+        PairRec<Real> rec;
+        rec.j = j; rec.nx = pg.nx; rec.ny = pg.ny; rec.w = pg.w;
+        if constexpr (sizeof(Real) == 8) rec.pad_ = 0;
+        pairs[(size_t)off + k] = rec;
         if constexpr (sizeof(Real) == 8) wl[k] = (double)pg.w; else psum += pg.w;
         const Real c = (1 - pg.w) * pg.w;
         const Real tx = c * pg.nx, ty = c * pg.ny;
@@ -243,49 +271,41 @@ k_density(const Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t 
 // K5: all forces, wall bounce, continuous collision and integration for particle s
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
-        const uint32_t *__restrict__ cell_start, const double2 *__restrict__ pos,
-        const typename Vec2<Real>::type *__restrict__ vel, const uint32_t *__restrict__ cell_key,
-        const uint32_t *__restrict__ uid, const double *__restrict__ host_noise,
-        const uint32_t *__restrict__ noise_off, const uint32_t *__restrict__ rank_of_uid,
-        const Real *__restrict__ pressure, const typename Vec2<Real>::type *__restrict__ tension,
-        const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
-        const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out,
-        typename Vec2<Real>::type *__restrict__ vel_out) {
+k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
+        const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
+        const PairRec<Real> *__restrict__ pairs, const uint32_t *__restrict__ pair_off,
+        const uint8_t *__restrict__ pair_cnt, const Real *__restrict__ pressure,
+        const typename Vec2<Real>::type *__restrict__ tension, const uint32_t *__restrict__ wall_bits,
+        const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
+        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out) {
     typedef typename Vec2<Real>::type R2;
-    const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    (void)cnt;
+    if (s >= *n_ptr) return;
     const double2 ps = pos[s];
-    const uint32_t uid_s = uid[s];
-    const uint32_t nbase = (P.noise_mode == SC_NOISE_HOST) ? noise_off[rank_of_uid[uid_s]] : 0u;
     const Real p_i = pressure[s];
     const R2 s_i = tension[s];
     const R2 v0 = vel[s];
+    const PairRec<Real> *__restrict__ mine = pairs + pair_off[s];
+    const int K = pair_cnt[s];
     const Real smooth = (Real)P.smooth, two_target = (Real)(2 * P.target);
     Real tx = 0, ty = 0;  // F3 sum
     Real qx = 0, qy = 0;  // F5 sum
-    Real sum_vx = 0, sum_vy = 0;         // fp32 mode: sum of neighbor velocities
-    __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
-    NbrList lst{s_list + threadIdx.x};
-    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
+    Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
     for (int k = 0; k < K; ++k) {
-        const uint32_t j = lst.get(k);
-        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
-        const Real p_j = pressure[j];
-        const R2 s_j = tension[j];
+        const PairRec<Real> rec = mine[k];
+        const Real p_j = pressure[rec.j];
+        const R2 s_j = tension[rec.j];
         // F3 pass 2, crate.py:347-353
         const Real ddx = s_i.x - s_j.x, ddy = s_i.y - s_j.y;
-        const Real align = (ddx * pg.nx + ddy * pg.ny) * smooth;
+        const Real align = (ddx * rec.nx + ddy * rec.ny) * smooth;
         const Real fix = p_j + p_i - two_target;
         const Real cc = align + fix;
-        const Real ex = cc * pg.nx, ey = cc * pg.ny;
+        const Real ex = cc * rec.nx, ey = cc * rec.ny;
         // F5, crate.py:301-306
         const Real ps_ = p_i + p_j;
-        const Real fx = pg.nx * ps_, fy = pg.ny * ps_;
+        const Real fx = rec.nx * ps_, fy = rec.ny * ps_;
         if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; } else { tx += ex; ty += ey; qx += fx; qy += fy; }
-        if constexpr (sizeof(Real) == 4) { const R2 vj = vel[j]; sum_vx += vj.x; sum_vy += vj.y; }
+        if constexpr (sizeof(Real) == 4) { const R2 vj = vel[rec.j]; sum_vx += vj.x; sum_vy += vj.y; }
     }
 
     // walls: contacts are recomputed from the position the particle had BEFORE apply_hard_wall_fix
@@ -299,11 +319,13 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
         for (int b = 0; b < W.nbodies; ++b) nb[b] = 0;
         for (int q = 0; q < W.S; ++q) {
             double cx, cy;
-            if (point_segment(pre.x, pre.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy) <= P.touch) nb[W.seg_body[q]]++;
+            if (point_segment(pre.x, pre.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy) <= P.touch)
+                nb[W.seg_body[q]]++;
         }
         for (int q = 0; q < W.S; ++q) {
             double cx, cy;
-            if (!(point_segment(pre.x, pre.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy) <= P.touch)) continue;
+            if (!(point_segment(pre.x, pre.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy) <= P.touch))
+                continue;
             const double vcx = (pre.x - cx) * 2, vcy = (pre.y - cy) * 2;  // crate.py:234, not normalised
             // W1b as written (crate.py:73-85): row V is overwritten by every body with more than V contacts
             double ux = 0, uy = 0;
@@ -335,7 +357,7 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
         Real ax = 0, ay = 0;
         if constexpr (sizeof(Real) == 8) {
             for (int q = 0; q < K; ++q) {
-                const R2 vj = vel[lst.get(q)];
+                const R2 vj = vel[mine[q].j];
                 const Real ex = vj.x - vx, ey = vj.y - vy;
                 if (q == 0) { ax = ex; ay = ey; } else { ax += ex; ay += ey; }
             }
@@ -363,22 +385,26 @@ k_force(const Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_cons
     {                                                                    // B2, crate.py:177-200
         const double mvx = dvx * P.dt, mvy = dvy * P.dt;
         const double bx = ps.x + mvx, by = ps.y + mvy;
-        const double bax = bx - ps.x, bay = by - ps.y;
         double f = 1.0;
         const double mxlo = fmin(ps.x, bx), mxhi = fmax(ps.x, bx), mylo = fmin(ps.y, by), myhi = fmax(ps.y, by);
-        for (int q = 0; q < 2 * W.S; ++q) {
-            if (mxhi < W.pad_box[q][0] || mxlo > W.pad_box[q][1] || myhi < W.pad_box[q][2] || mylo > W.pad_box[q][3])
-                continue;  // the movement cannot reach this padded segment
-            const double cx = W.pad[q][0], cy = W.pad[q][1], ex = W.pad[q][2], ey = W.pad[q][3];
-            const double cdx = ex - cx, cdy = ey - cy;
-            const bool opposite = (cdy * bax + (-cdx) * bay) < 0;        // geometry_utils.py:205
-            if (!opposite) continue;
-            const bool c1 = orientation(ps.x, ps.y, bx, by, cx, cy) != orientation(ps.x, ps.y, bx, by, ex, ey);
-            const bool c2 = orientation(cx, cy, ex, ey, ps.x, ps.y) != orientation(cx, cy, ex, ey, bx, by);
-            if (c1 && c2) {
-                const double acx = ps.x - cx, acy = ps.y - cy;
-                const double t = (acx * cdy - acy * cdx) / (cdx * mvy - cdy * mvx);  // geometry_utils.py:141-143
-                if (t < f) f = t;  // Python min(): NaN never wins (crate.py:199)
+        // one test for the bulk of the liquid: the movement stays inside a rectangle no padded segment reaches
+        const bool clear = mxlo > W.safe_ccd[0] && mxhi < W.safe_ccd[1] && mylo > W.safe_ccd[2] && myhi < W.safe_ccd[3];
+        if (!clear) {
+            const double bax = bx - ps.x, bay = by - ps.y;
+            for (int q = 0; q < 2 * W.S; ++q) {
+                if (mxhi < W.pad_box[q][0] || mxlo > W.pad_box[q][1] || myhi < W.pad_box[q][2] || mylo > W.pad_box[q][3])
+                    continue;  // the movement cannot reach this padded segment
+                const double cx = W.pad[q][0], cy = W.pad[q][1], ex = W.pad[q][2], ey = W.pad[q][3];
+                const double cdx = ex - cx, cdy = ey - cy;
+                const bool opposite = (cdy * bax + (-cdx) * bay) < 0;    // geometry_utils.py:205
+                if (!opposite) continue;
+                const bool c1 = orientation(ps.x, ps.y, bx, by, cx, cy) != orientation(ps.x, ps.y, bx, by, ex, ey);
+                const bool c2 = orientation(cx, cy, ex, ey, ps.x, ps.y) != orientation(cx, cy, ex, ey, bx, by);
+                if (c1 && c2) {
+                    const double acx = ps.x - cx, acy = ps.y - cy;
+                    const double t = (acx * cdy - acy * cdx) / (cdx * mvy - cdy * mvx);  // geometry_utils.py:141-143
+                    if (t < f) f = t;  // Python min(): NaN never wins (crate.py:199)
+                }
             }
         }
         dvx *= f; dvy *= f;

@@ -31,7 +31,10 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
         }
         int V = 0;
         double sx = 0, sy = 0;
-        for (int q = 0; q < W.S; ++q) {
+        // one test for the bulk of the liquid: inside a rectangle that no segment's touch zone reaches
+        const bool clear = p.x > W.safe_contact[0] && p.x < W.safe_contact[1] && p.y > W.safe_contact[2] &&
+                           p.y < W.safe_contact[3];
+        for (int q = 0; !clear && q < W.S; ++q) {
             if (p.x < W.seg_box[q][0] || p.x > W.seg_box[q][1] || p.y < W.seg_box[q][2] || p.y > W.seg_box[q][3])
                 continue;  // cannot be within the touch distance of this segment
             double cx, cy;
@@ -65,33 +68,6 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
 // exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply)
 #define SC_SCAN_ITEMS 8
 #define SC_SCAN_TILE (SC_BLOCK * SC_SCAN_ITEMS)
-
-__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
-    __shared__ uint32_t warp_sums[SC_BLOCK / 32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) warp_sums[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t w = lane < SC_BLOCK / 32 ? warp_sums[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < SC_BLOCK / 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += t;
-        }
-        if (lane < SC_BLOCK / 32) warp_sums[lane] = w;
-    }
-    __syncthreads();
-    const uint32_t base = wid ? warp_sums[wid - 1] : 0;
-    total = warp_sums[SC_BLOCK / 32 - 1];
-    __syncthreads();
-    return base + inc - v;
-}
 
 __global__ void __launch_bounds__(SC_BLOCK) k_scan_reduce(const uint32_t *__restrict__ a, uint32_t n,
                                                          uint32_t *__restrict__ bsum) {
@@ -325,7 +301,7 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
 }
 
 __global__ void k_begin_tick(Counters *cnt) {
-    cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0;
+    cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0;
 }
 
 template <typename Real>
