@@ -60,6 +60,7 @@ struct sc_ctx {
     bool in_step = false;     // between sc_step_begin and sc_step_finish
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
     bool lists_valid = false, rank_valid = false;
+    bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
     int64_t launches = 0;
     bool profiling = false;
     std::vector<ProfEvent> pending;
@@ -133,6 +134,7 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
     // one margin cell on every side so the 3x3 neighborhood never leaves the array
     Grid g;
     g.d = d;
+    g.inv_d = 1.0 / d;
     g.row_min = row_min - 1;
     g.col_min = col_min - 1;
     const int64_t nrows = (int64_t)row_max - row_min + 3, ncols = (int64_t)col_max - col_min + 3;
@@ -160,6 +162,7 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
 }
 
 static void refresh_wall_boxes(sc_ctx *ctx);
+static int sync_count(sc_ctx *ctx);
 
 static int refresh_dev_params(sc_ctx *ctx) {
     const sc_params &h = ctx->hp;
@@ -245,6 +248,7 @@ extern "C" int sc_set_params(sc_ctx *ctx, const sc_params *p) {
     if (!(p->particle_radius > 0) || !(p->dt == p->dt)) return fail(ctx, "sc_set_params: particle_radius must be > 0");
     const bool regrid = !ctx->params_set || p->particle_radius != ctx->hp.particle_radius;
     if (regrid && ctx->in_step) return fail(ctx, "sc_set_params: radius change inside a split step");
+    if (regrid && ctx->params_set) CKR(sync_count(ctx));  // the live count sits in the old cell array's tail
     ctx->hp = *p;
     refresh_dev_params(ctx);
     if (regrid) {
@@ -353,7 +357,14 @@ extern "C" int sc_set_tick(sc_ctx *ctx, uint64_t tick) {
     return 0;
 }
 
+__global__ void k_end_tick(Counters *cnt, const uint32_t *total) { cnt->n = *total; }
+
 static int sync_count(sc_ctx *ctx) {
+    if (ctx->carry_count) {  // a step ran since cnt->n was last written: its scan total is the live count
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
+        ctx->carry_count = false;
+    }
     if (ctx->n_exact) return 0;
     Counters h;
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -396,6 +407,7 @@ extern "C" int sc_set_state(sc_ctx *ctx, const double *pos, const double *vel, i
     if (ctx->in_step) return fail(ctx, "sc_set_state: inside a split step");
     ctx->next_uid = 0;
     ctx->srt_valid = false; ctx->lists_valid = false;
+    ctx->carry_count = false;  // the count is (re)defined by the host below
     const uint32_t zero = 0;
     CK(cudaMemcpyAsync(&ctx->cnt->n, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_host = 0; ctx->n_exact = true;
@@ -434,7 +446,7 @@ static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot) {
     ProfScope ps(ctx, slot);
     k_scan_reduce<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum);
     k_scan_sums<<<1, SC_BLOCK, 0, ctx->stream>>>(ctx->bsum, nb);
-    k_scan_apply<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum, nullptr);
+    k_scan_apply<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum);
     ctx->launches += 2;
     return 0;
 }
@@ -473,10 +485,11 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
     const Grid &g = ctx->grid;
     {
         ProfScope ps(ctx, SLOT_CLEAR);
-        k_begin_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt);
-        CK(cudaMemsetAsync(ctx->cell_start, 0, sizeof(uint32_t) * ((size_t)g.ncells + 1), ctx->stream));
-        CK(cudaMemsetAsync(ctx->wall_bits_cur, 0, sizeof(uint32_t) * ((size_t)ctx->cap / 32 + 1), ctx->stream));
-        CK(cudaMemsetAsync(ctx->wall_bits_srt, 0, sizeof(uint32_t) * ((size_t)ctx->cap / 32 + 1), ctx->stream));
+        const uint32_t words = (uint32_t)(n / 32 + 1);
+        const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
+        k_begin_tick<<<nb, SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start, g.ncells, ctx->carry_count ? 1 : 0,
+                                                       ctx->wall_bits_cur, ctx->wall_bits_srt, words);
+        ctx->carry_count = false;
     }
     if (n > 0) {
         ProfScope ps(ctx, SLOT_PREPASS);
@@ -534,8 +547,6 @@ static int enqueue_count(sc_ctx *ctx, const uint32_t *uid, bool want_lists) {
     return 0;
 }
 
-__global__ void k_end_tick(Counters *cnt, const uint32_t *total) { cnt->n = *total; }
-
 static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
     const int64_t n = ctx->n_host;
     const Grid &g = ctx->grid;
@@ -575,10 +586,7 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
                 (float2 *)ctx->vel_cur);
         }
     }
-    {
-        ProfScope ps(ctx, SLOT_END);
-        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + g.ncells);
-    }
+    ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
     CK(cudaGetLastError());
     // the new state (pos_cur, vel_cur) is in this tick's sorted order, whose uids are uid_srt
     uint32_t *t = ctx->uid_cur; ctx->uid_cur = ctx->uid_srt; ctx->uid_srt = t;
@@ -843,7 +851,7 @@ extern "C" int sc_detect_particle_collisions(sc_ctx *parent, const double *parti
         if (cudaMalloc((void **)&db, sizeof(hb)) != cudaSuccess) { rc = fail(t, "cudaMalloc bounds"); break; }
         cudaMemcpyAsync(db, hb, sizeof(hb), cudaMemcpyHostToDevice, t->stream);
         // upload without a grid yet
-        t->grid.d = diameter;
+        t->grid.d = diameter; t->grid.inv_d = 1.0 / diameter;
         if ((rc = upload_particles(t, particles, zeros.data(), 0, P))) { cudaFree(db); break; }
         k_cell_bounds<<<blocks_for(P), SC_BLOCK, 0, t->stream>>>(t->pos_cur, (uint32_t)P, diameter, db);
         cudaMemcpyAsync(hb, db, sizeof(hb), cudaMemcpyDeviceToHost, t->stream);

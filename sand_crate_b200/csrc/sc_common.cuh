@@ -20,6 +20,7 @@ namespace sc {
 // (row, col, x, uid) is the same permutation as np.lexsort((x, row)), collision_detector.py:127).
 struct Grid {
     double d;          // diameter
+    double inv_d;      // 1 / d, only used to pre-screen floor(y / d) (see cell_of)
     int row_min;       // cell row index = row - row_min, clamped to [1, nrows - 2]
     int col_min;
     int nrows;
@@ -105,9 +106,21 @@ __device__ inline double orientation(double px, double py, double qx, double qy,
     return sign_np(((qy - py) * (rx - qx)) - ((qx - px) * (ry - qy)));  // geometry_utils.py:212-222
 }
 
+// floor(v / d) exactly as NumPy computes it (collision_detector.py:126), without paying for an fp64 division on
+// every particle: v * (1/d) and v / d differ by at most a couple of ulps, so their floors can only differ when the
+// product lands within that distance of an integer - only then is the true division evaluated.
+static __device__ __noinline__ double floor_div_exact(double v, double d) { return floor(v / d); }
+__device__ __forceinline__ double floor_div(double v, const Grid &g) {
+    const double q = v * g.inv_d;
+    const double f = floor(q);
+    const double near = fmin(q - f, (f + 1.0) - q);
+    if (!(near > fabs(q) * 1e-14)) return floor_div_exact(v, g.d);  // also NaN / inf
+    return f;
+}
+
 // cell of a position; NaN / out-of-grid coordinates are clamped into the margin cells
 __device__ inline uint32_t cell_of(const Grid &g, double x, double y, int &row_out) {
-    const double fr = floor(y / g.d), fc = floor(x / g.d);
+    const double fr = floor_div(y, g), fc = floor_div(x, g);
     int row = (fr >= -2.0e9 && fr <= 2.0e9) ? (int)fr : 0;
     int col = (fc >= -2.0e9 && fc <= 2.0e9) ? (int)fc : 0;
     row_out = row;

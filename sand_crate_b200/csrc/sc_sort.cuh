@@ -65,17 +65,33 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply)
-#define SC_SCAN_ITEMS 8
+// exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply).
+// 16 items per thread as four 128-bit accesses: a warp request covers 2 KB contiguous.
+#define SC_SCAN_ITEMS 16
 #define SC_SCAN_TILE (SC_BLOCK * SC_SCAN_ITEMS)
+
+__device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {
+    if (base + SC_SCAN_ITEMS <= n) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(a + base);  // base is a multiple of 16 items
+#pragma unroll
+        for (int q = 0; q < SC_SCAN_ITEMS / 4; ++q) {
+            const uint4 v = p[q];
+            item[4 * q] = v.x; item[4 * q + 1] = v.y; item[4 * q + 2] = v.z; item[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < SC_SCAN_ITEMS; ++q) item[q] = (base + q < n) ? a[base + q] : 0u;
+    }
+}
 
 __global__ void __launch_bounds__(SC_BLOCK) k_scan_reduce(const uint32_t *__restrict__ a, uint32_t n,
                                                          uint32_t *__restrict__ bsum) {
     const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
+    uint32_t item[SC_SCAN_ITEMS];
+    scan_load(a, n, base, item);
     uint32_t v = 0;
 #pragma unroll
-    for (int q = 0; q < SC_SCAN_ITEMS; ++q)
-        if (base + q < n) v += a[base + q];
+    for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
     uint32_t total;
     block_exclusive_scan(v, total);
     if (threadIdx.x == 0) bsum[blockIdx.x] = total;
@@ -97,27 +113,31 @@ __global__ void __launch_bounds__(SC_BLOCK) k_scan_sums(uint32_t *__restrict__ b
 }
 
 __global__ void __launch_bounds__(SC_BLOCK) k_scan_apply(uint32_t *__restrict__ a, uint32_t n,
-                                                        const uint32_t *__restrict__ bsum,
-                                                        uint32_t *__restrict__ n_out) {
+                                                        const uint32_t *__restrict__ bsum) {
     const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
     uint32_t item[SC_SCAN_ITEMS];
+    scan_load(a, n, base, item);
     uint32_t v = 0;
 #pragma unroll
-    for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
-        item[q] = (base + q < n) ? a[base + q] : 0;
-        v += item[q];
-    }
+    for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
     uint32_t total;
     uint32_t run = block_exclusive_scan(v, total) + bsum[blockIdx.x];
 #pragma unroll
     for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
-        if (base + q < n) a[base + q] = run;
-        run += item[q];
+        const uint32_t t = item[q];
+        item[q] = run;
+        run += t;
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SC_BLOCK - 1) {
-        a[n] = run;  // grand total (all out-of-range items are 0)
-        if (n_out) *n_out = run;
+    if (base + SC_SCAN_ITEMS <= n) {
+        uint4 *p = reinterpret_cast<uint4 *>(a + base);
+#pragma unroll
+        for (int q = 0; q < SC_SCAN_ITEMS / 4; ++q) p[q] = make_uint4(item[4 * q], item[4 * q + 1], item[4 * q + 2], item[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < SC_SCAN_ITEMS; ++q)
+            if (base + q < n) a[base + q] = item[q];
     }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SC_BLOCK - 1) a[n] = run;  // grand total
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -300,8 +320,22 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
     if (i < n) a[i] = base + i;
 }
 
-__global__ void k_begin_tick(Counters *cnt) {
-    cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0;
+// Start of a tick, one launch: carry the live count over from the previous tick's scan total (when the host has
+// not touched the particle set in between), reset the per-tick counters, zero the cell histogram and both wall
+// bitmaps.  Entry [ncells] (the previous total) is deliberately not zeroed: the scan rewrites it.
+__global__ void __launch_bounds__(SC_BLOCK)
+k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, int carry_count,
+             uint32_t *__restrict__ bits_a, uint32_t *__restrict__ bits_b, uint32_t nbits_words) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        if (carry_count) cnt->n = cell_count[ncells];
+        cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0;
+    }
+    uint4 *c4 = reinterpret_cast<uint4 *>(cell_count);
+    const uint32_t n4 = ncells / 4;
+    for (uint32_t i = tid; i < n4; i += nth) c4[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = n4 * 4 + tid; i < ncells; i += nth) cell_count[i] = 0;
+    for (uint32_t i = tid; i < nbits_words; i += nth) { bits_a[i] = 0; bits_b[i] = 0; }
 }
 
 template <typename Real>
