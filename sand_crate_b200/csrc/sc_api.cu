@@ -39,13 +39,14 @@ struct sc_ctx {
     uint64_t seed = 0, tick = 0;
     // particle state: *_cur = current state (order left by the previous tick), *_srt = this tick's sorted gather
     double2 *pos_cur = nullptr, *pos_srt = nullptr;
+    float2 *rel_srt = nullptr;        // cell-relative fp32 positions of the sorted set
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
     uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
     uint32_t *cell_start = nullptr; size_t cell_cap = 0;
     uint32_t *bsum = nullptr; size_t bsum_cap = 0;
-    void *pressure = nullptr, *tension = nullptr;
-    void *pairs = nullptr;            // PairRec<Real>[cap * SC_MAX_NEIGHBORS], written by K4, read by K5
+    void *ps = nullptr;               // PS<Real>[cap]: pressure + surface normal of the sorted set
+    uint32_t *pair_j = nullptr; void *pair_n = nullptr;  // [cap * SC_MAX_NEIGHBORS], written by K4, read by K5
     uint32_t *pair_off = nullptr; uint8_t *pair_cnt = nullptr;
     uint32_t *wall_bits_cur = nullptr, *wall_bits_srt = nullptr, *wall_slot_cur = nullptr, *wall_slot_srt = nullptr;
     double2 *wall_pre = nullptr;
@@ -185,7 +186,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     if (!out) return fail(nullptr, "sc_create: out is NULL");
     *out = nullptr;
     if (precision != SC_PRECISION_F64 && precision != SC_PRECISION_MIXED) return fail(nullptr, "sc_create: bad precision");
-    if (capacity < 1 || capacity > ((int64_t)1 << 31) - 1) return fail(nullptr, "sc_create: capacity out of range");
+    if (capacity < 1 || capacity > (int64_t)SC_IDX_MASK) return fail(nullptr, "sc_create: capacity out of range");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -211,8 +212,10 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, &c->uid_cur, n); rc |= dev_alloc(c, &c->uid_srt, n);
     rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
     rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
-    rc |= dev_alloc(c, (char **)&c->pressure, n * rs); rc |= dev_alloc(c, (char **)&c->tension, n * 2 * rs);
-    rc |= dev_alloc(c, (char **)&c->pairs, n * SC_MAX_NEIGHBORS * (rs == 8 ? 32 : 16));
+    rc |= dev_alloc(c, &c->rel_srt, n);
+    rc |= dev_alloc(c, (char **)&c->ps, n * 4 * rs);
+    rc |= dev_alloc(c, &c->pair_j, n * SC_MAX_NEIGHBORS);
+    rc |= dev_alloc(c, (char **)&c->pair_n, n * SC_MAX_NEIGHBORS * 2 * rs);
     rc |= dev_alloc(c, &c->pair_off, n); rc |= dev_alloc(c, &c->pair_cnt, n);
     rc |= dev_alloc(c, &c->wall_bits_cur, n / 32 + 1); rc |= dev_alloc(c, &c->wall_bits_srt, n / 32 + 1);
     rc |= dev_alloc(c, &c->wall_slot_cur, n); rc |= dev_alloc(c, &c->wall_slot_srt, n);
@@ -232,7 +235,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->pressure, c->tension, c->pairs, c->pair_off, c->pair_cnt,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -508,12 +511,12 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         if (ctx->precision == SC_PRECISION_F64)
             k_rank_gather<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
-                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, (double2 *)ctx->vel_srt,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
                 ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
         else
             k_rank_gather<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
-                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, (float2 *)ctx->vel_srt,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
                 ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
     }
     CK(cudaGetLastError());
@@ -539,7 +542,7 @@ static int enqueue_count(sc_ctx *ctx, const uint32_t *uid, bool want_lists) {
     if (n > 0) {
         ProfScope ps(ctx, SLOT_COUNT);
         k_count_neighbors<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-            ctx->cnt, ctx->grid, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, uid, ctx->rank_of_uid,
+            ctx->cnt, ctx->grid, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, uid, ctx->rank_of_uid,
             ctx->count_by_rank, want_lists ? ctx->list_sorted : nullptr);
     }
     CK(cudaGetLastError());
@@ -560,30 +563,28 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 k_density<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
-                    noise_off, ctx->rank_of_uid, (PairRec<double> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt,
-                    (double *)ctx->pressure, (double2 *)ctx->tension);
+                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
+                    ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (double2 *)ctx->pair_n, ctx->pair_off,
+                    ctx->pair_cnt, (PS<double> *)ctx->ps);
             }
             ProfScope ps(ctx, SLOT_FORCE);
             k_force<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                n_ptr, dp, ctx->walls, ctx->pos_srt, (const double2 *)ctx->vel_srt,
-                (const PairRec<double> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt, (const double *)ctx->pressure,
-                (const double2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
-                (double2 *)ctx->vel_cur);
+                n_ptr, dp, ctx->walls, ctx->pos_srt, (const double2 *)ctx->vel_srt, ctx->pair_j,
+                (const double2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<double> *)ctx->ps,
+                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur);
         } else {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 k_density<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev,
-                    noise_off, ctx->rank_of_uid, (PairRec<float> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt,
-                    (float *)ctx->pressure, (float2 *)ctx->tension);
+                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
+                    ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (float2 *)ctx->pair_n, ctx->pair_off,
+                    ctx->pair_cnt, (PS<float> *)ctx->ps);
             }
             ProfScope ps(ctx, SLOT_FORCE);
             k_force<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                n_ptr, dp, ctx->walls, ctx->pos_srt, (const float2 *)ctx->vel_srt,
-                (const PairRec<float> *)ctx->pairs, ctx->pair_off, ctx->pair_cnt, (const float *)ctx->pressure,
-                (const float2 *)ctx->tension, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
-                (float2 *)ctx->vel_cur);
+                n_ptr, dp, ctx->walls, ctx->pos_srt, (const float2 *)ctx->vel_srt, ctx->pair_j,
+                (const float2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps,
+                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur);
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
@@ -704,9 +705,9 @@ extern "C" int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *press
         } else {
             ProfScope ps(ctx, SLOT_IO);
             if (ctx->precision == SC_PRECISION_F64)
-                k_scatter_scalar<double><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const double *)ctx->pressure, ctx->stage1);
+                k_scatter_ps<double><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const PS<double> *)ctx->ps, ctx->stage1, nullptr);
             else
-                k_scatter_scalar<float><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const float *)ctx->pressure, ctx->stage1);
+                k_scatter_ps<float><<<nb, SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->uid_cur, ctx->rank_of_uid, (const PS<float> *)ctx->ps, ctx->stage1, nullptr);
         }
         CK(cudaMemcpyAsync(pressure, ctx->stage1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -804,9 +805,9 @@ extern "C" int sc_get_tension(sc_ctx *ctx, double *tension, int64_t cap) {
     const uint32_t *n_ptr = ctx->cell_start + ctx->grid.ncells;
     { ProfScope ps(ctx, SLOT_IO);
       if (ctx->precision == SC_PRECISION_F64)
-          k_scatter_vec2<double2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const double2 *)ctx->tension, ctx->stage2);
+          k_scatter_ps<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const PS<double> *)ctx->ps, nullptr, ctx->stage2);
       else
-          k_scatter_vec2<float2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const float2 *)ctx->tension, ctx->stage2); }
+          k_scatter_ps<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const PS<float> *)ctx->ps, nullptr, ctx->stage2); }
     CK(cudaMemcpyAsync(tension, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());

@@ -1,14 +1,14 @@
 // sc_pair.cuh - the two fused pair kernels (density, force+integrate), templated on the arithmetic type.
 //
 //   k_density  (K4)  collision_detector.py:52-121 pair discovery fused with crate.py:161-175 (populate_colliders),
-//                    261-275 (pressure) and 337-342 (surface normals)
+//                    261-275 (pressure) and 337-342 (surface normals); emits one record per directed pair
 //   k_force    (K5)  crate.py:343-353 tension, 309-310 gravity, 295-307 pressure, 316-323 viscosity,
 //                    245-259 wall bounce, 177-200 continuous collision, 360-361 integration
 //
-// Both walk, for the particle at sorted index s, the three contiguous sorted ranges that cover the 3x3 cells
-// around it and visit accepted neighbors in EXACTLY the reference's list order:
-//   same row ascending from s+1, next row ascending, same row descending from s-1, previous row descending,
-// first 20 only.  Every neighbor quantity read is a start-of-tick snapshot (Jacobi), so there are no atomics.
+// K4 walks, for the particle at sorted index s, the 3x3 cells around it and collects accepted neighbors in EXACTLY
+// the reference's list order: same row ascending from s+1, next row ascending, same
+// row descending from s-1, previous row descending, first 20 only.  Every neighbor quantity read is a
+// start-of-tick snapshot (Jacobi), so there are no atomics on particle data.
 #pragma once
 #include "sc_common.cuh"
 
@@ -18,85 +18,80 @@ template <typename Real> struct Vec2;
 template <> struct Vec2<double> { typedef double2 type; };
 template <> struct Vec2<float> { typedef float2 type; };
 
-__device__ inline double sc_sqrt(double v) { return sqrt(v); }
-__device__ inline float sc_sqrt(float v) { return sqrtf(v); }
+// pressure and surface normal of one particle, written by K4 as one vector store and gathered by K5 as one load
+template <typename Real> struct PS;
+template <> struct __align__(16) PS<float> { float p, sx, sy, pad_; };
+template <> struct __align__(32) PS<double> { double p, sx, sy, pad_; };
 
 // Per-thread neighbor list kept in shared memory, one column per thread (conflict-free: slot k of thread t is
-// word k * SC_BLOCK + t).
+// word k * SC_BLOCK + t).  An entry is the neighbor's sorted index in the low 28 bits and the relative cell
+// (dr + 1) * 3 + (dc + 1) in the high 4.
+#define SC_IDX_MASK 0x0FFFFFFFu
 struct NbrList {
     uint32_t *col;
     __device__ __forceinline__ uint32_t get(int k) const { return col[k * SC_BLOCK]; }
-    __device__ __forceinline__ void set(int k, uint32_t j) { col[k * SC_BLOCK] = j; }
+    __device__ __forceinline__ void set(int k, uint32_t e) { col[k * SC_BLOCK] = e; }
 };
 
-// The reference accepts a pair iff sqrt(dx*dx + dy*dy) <= d in fp64 (collision_detector.py:77-79).  q = dx*dx+dy*dy
-// is formed exactly as NumPy forms it; sqrt is correctly rounded and monotone, so outside a 2^-40 relative band
-// around d*d the outcome is decided by q alone and the fp64 sqrt (about 30 instructions) is only evaluated inside
-// the band - bit-identical decisions, including the lattice cases that sit exactly on q == d*d.
-struct AcceptBand {
-    double d, d2_lo, d2_hi;
-    __device__ __forceinline__ explicit AcceptBand(double d_) : d(d_) {
-        const double d2 = d_ * d_;
-        d2_lo = d2 * (1.0 - 9.094947017729282e-13);  // 2^-40
-        d2_hi = d2 * (1.0 + 9.094947017729282e-13);
-    }
-    __device__ __forceinline__ bool operator()(double dx, double dy) const {
-        const double q = dx * dx + dy * dy;
-        if (q > d2_hi) return false;
-        if (q < d2_lo) return true;
-        return in_band(q, d);  // also where NaN ends up: false, like the reference
-    }
-    // out of line on purpose: inlined, ptxas hoists the fp64 sqrt sequence in front of the two fast exits
-    static __device__ __noinline__ bool in_band(double q, double d) { return sqrt(q) <= d; }
-};
+// The reference's acceptance of a candidate pair, bit for bit: the x-window evaluated from the LOWER-sorted particle
+// (collision_detector.py:106-119) and sqrt(dx*dx + dy*dy) <= d in fp64 (collision_detector.py:77-79).  Out of line:
+// it only runs for candidates whose fp32 distance estimate falls inside a narrow band around d (see below).
+static __device__ __noinline__ bool accept_exact(double2 ps, double2 pj, double d, int dr, bool fwd) {
+    const double xlo = fwd ? ps.x : pj.x, xhi = fwd ? pj.x : ps.x;
+    const double ylo = fwd ? ps.y : pj.y, yhi = fwd ? pj.y : ps.y;
+    if (dr == 0) { if (!(xhi <= xlo + d)) return false; }
+    else { if (!(xlo - d <= xhi && xhi <= xlo + d)) return false; }
+    const double dx = xhi - xlo, dy = yhi - ylo;
+    return sqrt(dx * dx + dy * dy) <= d;
+}
 
-// Phase 1 of both pair kernels: collects the neighbors of sorted particle s in EXACTLY the reference's list order
-// into `lst` and returns their number (<= 20).  Acceptance is evaluated in fp64 in both precision modes: the
-// x-window from the LOWER-sorted particle (collision_detector.py:106-119) and the distance test above.
-__device__ __forceinline__ int collect_neighbors(uint32_t s, double2 ps, uint32_t c, const Grid &g,
+// Phase 1 of K4.  Candidates are screened in fp32 on CELL-RELATIVE coordinates (`rel` = position minus the origin of
+// the particle's own cell, |rel| < d, so an fp32 holds it to 6e-8 d): squared distance outside [1 - 4e-6, 1 + 4e-6]
+// d^2 decides by itself (the fp32 evaluation error is below 1e-6 d^2, and a pair that close to or that far inside d
+// passes / fails the reference's x-window as well); inside the band the reference's own fp64 arithmetic is replayed
+// (accept_exact).  The decisions are therefore bit-identical to the reference's in both precision modes, and the
+// bulk of the liquid never touches an fp64 instruction here.  Cell visiting order = reference list order:
+//   forward : (0,0) beyond s, (0,+1), (+1,-1), (+1,0), (+1,+1)   ascending
+//   backward: (0,0) before s, (0,-1), (-1,+1), (-1,0), (-1,-1)   descending            [(dr, dc), mirrored]
+__device__ __forceinline__ int collect_neighbors(uint32_t s, uint32_t c, const Grid &g,
                                                  const uint32_t *__restrict__ cell_start,
-                                                 const double2 *__restrict__ pos, NbrList lst) {
-    const double d = g.d;
-    const AcceptBand accept(d);
+                                                 const float2 *__restrict__ rel, const double2 *__restrict__ pos,
+                                                 NbrList lst) {
+    const float df = (float)g.d;
+    const float hi = (df * df) * (1.0f + 4e-6f), lo = (df * df) * (1.0f - 4e-6f);
+    const float2 rs = rel[s];
+    // the 12 cell boundaries of the 3x3 block, loaded up front (independent loads)
+    const uint32_t *cs0 = cell_start + c - 1, *csn = cs0 + g.ncols, *csp = cs0 - g.ncols;
+    const uint32_t m0 = cs0[0], m1 = cs0[1], m2 = cs0[2], m3 = cs0[3];
+    const uint32_t n0 = csn[0], n1 = csn[1], n2 = csn[2], n3 = csn[3];
+    const uint32_t p0 = csp[0], p1 = csp[1], p2 = csp[2], p3 = csp[3];
+    // four contiguous sorted ranges, each three cells wide (per-thread trip counts in a warp are alike even though
+    // per-cell counts are not, so the warp stays converged):
+    //   (s, m3) ascending, [n0, n3) ascending, [m0, s) descending, [p0, p3) descending
     int count = 0;
-    const uint32_t a1 = cell_start[c + 2];
-    const uint32_t cn = c + (uint32_t)g.ncols, cp = c - (uint32_t)g.ncols;
-    const double xs_hi = ps.x + d, xs_lo = ps.x - d;
-    // same row, ascending from s + 1
-    for (uint32_t j = s + 1; j < a1 && count < SC_MAX_NEIGHBORS; ++j) {
-        const double2 pj = pos[j];
-        if (!(pj.x <= xs_hi)) break;  // sorted by x inside the row: nothing further can pass the window
-        if (accept(pj.x - ps.x, pj.y - ps.y)) lst.set(count++, j);
+#define SC_SCAN_RANGE(FIRST, STOP, B1, B2, DR, ASC)                                                              \
+    {                                                                                                            \
+        const float by = rs.y - (float)(DR) * df;                                                                \
+        /* count < 20 in the loop condition = trim_collisions, collision_detector.py:91-93 */                   \
+        for (uint32_t j = (FIRST); j != (STOP) && count < SC_MAX_NEIGHBORS; j += (ASC) ? 1u : 0xFFFFFFFFu) {     \
+            const float2 rj = rel[j];                                                                            \
+            /* x offset of the candidate's cell column relative to ours: (rel_j + (dc, dr) d) - rel_s */         \
+            const float ox = (j >= (B2)) ? df : ((j >= (B1)) ? 0.0f : -df);                                      \
+            const float dx = (rj.x + ox) - rs.x, dy = rj.y - by;                                                 \
+            const float qd = fmaf(dx, dx, dy * dy);                                                              \
+            /* qd > hi: surely farther than d (NaN lands here too: the reference rejects NaN); qd < lo: inside */ \
+            if (qd <= hi && (qd < lo || accept_exact(pos[s], pos[j], g.d, (DR), (ASC)))) {                       \
+                const int dc = (int)(j >= (B1)) + (int)(j >= (B2)) - 1;                                          \
+                lst.set(count, j | ((uint32_t)(((DR) + 1) * 3 + (dc + 1)) << 28));                               \
+                ++count;                                                                                         \
+            }                                                                                                    \
+        }                                                                                                        \
     }
-    // next row, ascending
-    {
-        const uint32_t b0 = cell_start[cn - 1], b1 = cell_start[cn + 2];
-        for (uint32_t j = b0; j < b1 && count < SC_MAX_NEIGHBORS; ++j) {
-            const double2 pj = pos[j];
-            if (!(xs_lo <= pj.x && pj.x <= xs_hi)) continue;
-            if (accept(pj.x - ps.x, pj.y - ps.y)) lst.set(count++, j);
-        }
-    }
-    // same row, descending from s - 1: j is the lower-sorted one, so the window is evaluated from j
-    {
-        const uint32_t a0 = cell_start[c - 1];
-        for (uint32_t j = s; j > a0 && count < SC_MAX_NEIGHBORS;) {
-            --j;
-            const double2 pj = pos[j];
-            if (!(ps.x <= pj.x + d)) break;
-            if (accept(ps.x - pj.x, ps.y - pj.y)) lst.set(count++, j);
-        }
-    }
-    // previous row, descending
-    {
-        const uint32_t c0 = cell_start[cp - 1], c1 = cell_start[cp + 2];
-        for (uint32_t j = c1; j > c0 && count < SC_MAX_NEIGHBORS;) {
-            --j;
-            const double2 pj = pos[j];
-            if (!(pj.x - d <= ps.x && ps.x <= pj.x + d)) continue;
-            if (accept(ps.x - pj.x, ps.y - pj.y)) lst.set(count++, j);
-        }
-    }
+    SC_SCAN_RANGE(s + 1, m3, m1, m2, 0, true)
+    SC_SCAN_RANGE(n0, n3, n1, n2, 1, true)
+    SC_SCAN_RANGE(s - 1, m0 - 1, m1, m2, 0, false)
+    SC_SCAN_RANGE(p3 - 1, p0 - 1, p1, p2, -1, false)
+#undef SC_SCAN_RANGE
     return count;
 }
 
@@ -104,16 +99,9 @@ __device__ __forceinline__ int collect_neighbors(uint32_t s, double2 ps, uint32_
 // w = 1 - clip(dist / d, 0, 1) (crate.py:270).
 template <typename Real> struct PairGeom { Real nx, ny, w; };
 
-template <typename Real>
-__device__ __forceinline__ PairGeom<Real> pair_geom(const DevParams &P, double2 pi, double2 pj, uint32_t uid_i,
-                                                    uint32_t uid_j, const double *__restrict__ host_noise,
-                                                    uint32_t noise_index);
-
-template <>
-__device__ __forceinline__ PairGeom<double> pair_geom<double>(const DevParams &P, double2 pi, double2 pj,
-                                                              uint32_t uid_i, uint32_t uid_j,
-                                                              const double *__restrict__ host_noise,
-                                                              uint32_t noise_index) {
+__device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, double2 pi, double2 pj, uint32_t uid_i,
+                                                          uint32_t uid_j, const double *__restrict__ host_noise,
+                                                          uint32_t noise_index) {
     double qx = pj.x, qy = pj.y;
     if (P.noise_mode != SC_NOISE_NONE) {
         double ux, uy;
@@ -141,14 +129,11 @@ __device__ __forceinline__ PairGeom<double> pair_geom<double>(const DevParams &P
     return g;
 }
 
-template <>
-__device__ __forceinline__ PairGeom<float> pair_geom<float>(const DevParams &P, double2 pi, double2 pj,
-                                                            uint32_t uid_i, uint32_t uid_j,
-                                                            const double *__restrict__ host_noise,
-                                                            uint32_t noise_index) {
-    // the difference is formed in fp64 (absolute fp32 coordinates lose 1e-4-level precision in the weights at
-    // d ~ 1e-4), everything after it is fp32
-    float rx = (float)(pi.x - pj.x), ry = (float)(pi.y - pj.y);
+// fp32 flavour: (rx, ry) = p_i - p_j formed from the cell-relative coordinates (absolute fp32 coordinates would lose
+// 1e-4-level precision in the weights at d ~ 1e-4)
+__device__ __forceinline__ PairGeom<float> pair_geom_f32(const DevParams &P, float rx, float ry, uint32_t uid_i,
+                                                         uint32_t uid_j, const double *__restrict__ host_noise,
+                                                         uint32_t noise_index) {
     if (P.noise_mode != SC_NOISE_NONE) {
         float ux, uy;
         if (P.noise_mode == SC_NOISE_HOST) {
@@ -199,34 +184,27 @@ __device__ inline double np_sum_1d(const double *a, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// One record per directed pair (i <- j), produced by K4 and consumed by K5, so the pair geometry - including the
-// noise hash and the reciprocal square root - is evaluated once per tick instead of twice.  HBM is the idle
-// resource on this path (the kernels are issue-bound), so 16 bytes per pair are a good trade.
-template <typename Real> struct PairRec;
-template <> struct __align__(16) PairRec<float> { uint32_t j; float nx, ny, w; };
-template <> struct __align__(16) PairRec<double> { double nx, ny, w; uint32_t j, pad_; };
-
-// K4: neighbor discovery, pair geometry, pressure p_i and surface normal s_i
+// K4: neighbor discovery, pair geometry, pressure p_i and surface normal s_i.
+// One record per directed pair (i <- j) goes to the pair buffer (pair_j: neighbor index, pair_n: unit vector) and
+// is consumed by K5, so the pair geometry - noise hash, reciprocal square root - is evaluated once per tick instead
+// of twice.  HBM is the idle resource on this path (the kernels are issue / L1 bound), so 12 bytes per pair are a
+// good trade.
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
-          const double2 *__restrict__ pos, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ uid,
-          const double *__restrict__ host_noise, const uint32_t *__restrict__ noise_off,
-          const uint32_t *__restrict__ rank_of_uid, PairRec<Real> *__restrict__ pairs,
-          uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, Real *__restrict__ pressure,
-          typename Vec2<Real>::type *__restrict__ tension) {
+          const double2 *__restrict__ pos, const float2 *__restrict__ rel, const uint32_t *__restrict__ cell_key,
+          const uint32_t *__restrict__ uid, const double *__restrict__ host_noise,
+          const uint32_t *__restrict__ noise_off, const uint32_t *__restrict__ rank_of_uid,
+          uint32_t *__restrict__ pair_j, typename Vec2<Real>::type *__restrict__ pair_n,
+          uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, PS<Real> *__restrict__ ps_out) {
     __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
     __shared__ uint32_t s_base;
     const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < n;
     NbrList lst{s_list + threadIdx.x};
-    double2 ps = make_double2(0, 0);
     int K = 0;
-    if (live) {
-        ps = pos[s];
-        K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
-    }
+    if (live) K = collect_neighbors(s, cell_key[s], g, cell_start, rel, pos, lst);
     // the block's records go to one contiguous chunk of the pair buffer (one atomic per block; where the chunk
     // lands is arbitrary, but it is only ever reached through pair_off, so results do not depend on it)
     uint32_t total;
@@ -242,13 +220,27 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
     Real ax = 0, ay = 0;
     Real psum = 0;
     double wl[sizeof(Real) == 8 ? SC_MAX_NEIGHBORS : 1];  // fp64 only: np.sum's pairwise order needs the list
+    double2 ps64 = make_double2(0, 0);
+    float2 rs = make_float2(0, 0);
+    float df = 0;
+    if constexpr (sizeof(Real) == 8) ps64 = pos[s]; else { rs = rel[s]; df = (float)g.d; }
     for (int k = 0; k < K; ++k) {
-        const uint32_t j = lst.get(k);
-        const PairGeom<Real> pg = pair_geom<Real>(P, ps, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
-        PairRec<Real> rec;
-        rec.j = j; rec.nx = pg.nx; rec.ny = pg.ny; rec.w = pg.w;
-        if constexpr (sizeof(Real) == 8) rec.pad_ = 0;
-        pairs[(size_t)off + k] = rec;
+        const uint32_t e = lst.get(k);
+        const uint32_t j = e & SC_IDX_MASK;
+        PairGeom<Real> pg;
+        if constexpr (sizeof(Real) == 8) {
+            pg = pair_geom_f64(P, ps64, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+        } else {
+            const int code = (int)(e >> 28);
+            const float2 rj = rel[j];
+            const float rx = (rs.x - rj.x) - (float)(code % 3 - 1) * df;
+            const float ry = (rs.y - rj.y) - (float)(code / 3 - 1) * df;
+            pg = pair_geom_f32(P, rx, ry, uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+        }
+        pair_j[(size_t)off + k] = j;
+        typename Vec2<Real>::type nv;
+        nv.x = pg.nx; nv.y = pg.ny;
+        pair_n[(size_t)off + k] = nv;
         if constexpr (sizeof(Real) == 8) wl[k] = (double)pg.w; else psum += pg.w;
         const Real c = (1 - pg.w) * pg.w;
         const Real tx = c * pg.nx, ty = c * pg.ny;
@@ -261,10 +253,9 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
         else pr = psum - (Real)P.ignored;
         p = (pr > 0 || pr != pr) ? pr : (Real)0;  // np.maximum(0, pr), crate.py:273
     }
-    pressure[s] = p;
-    typename Vec2<Real>::type t;
-    t.x = ax; t.y = ay;
-    tension[s] = t;
+    PS<Real> o;
+    o.p = p; o.sx = ax; o.sy = ay; o.pad_ = 0;
+    ps_out[s] = o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -273,39 +264,58 @@ template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
         const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
-        const PairRec<Real> *__restrict__ pairs, const uint32_t *__restrict__ pair_off,
-        const uint8_t *__restrict__ pair_cnt, const Real *__restrict__ pressure,
-        const typename Vec2<Real>::type *__restrict__ tension, const uint32_t *__restrict__ wall_bits,
+        const uint32_t *__restrict__ pair_j, const typename Vec2<Real>::type *__restrict__ pair_n,
+        const uint32_t *__restrict__ pair_off, const uint8_t *__restrict__ pair_cnt,
+        const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
         const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
         double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out) {
     typedef typename Vec2<Real>::type R2;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     const double2 ps = pos[s];
-    const Real p_i = pressure[s];
-    const R2 s_i = tension[s];
+    const PS<Real> me = ps_in[s];
+    const Real p_i = me.p;
     const R2 v0 = vel[s];
-    const PairRec<Real> *__restrict__ mine = pairs + pair_off[s];
+    const uint32_t off = pair_off[s];
     const int K = pair_cnt[s];
     const Real smooth = (Real)P.smooth, two_target = (Real)(2 * P.target);
     Real tx = 0, ty = 0;  // F3 sum
     Real qx = 0, qy = 0;  // F5 sum
     Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
-    for (int k = 0; k < K; ++k) {
-        const PairRec<Real> rec = mine[k];
-        const Real p_j = pressure[rec.j];
-        const R2 s_j = tension[rec.j];
-        // F3 pass 2, crate.py:347-353
-        const Real ddx = s_i.x - s_j.x, ddy = s_i.y - s_j.y;
-        const Real align = (ddx * rec.nx + ddy * rec.ny) * smooth;
-        const Real fix = p_j + p_i - two_target;
-        const Real cc = align + fix;
-        const Real ex = cc * rec.nx, ey = cc * rec.ny;
-        // F5, crate.py:301-306
-        const Real ps_ = p_i + p_j;
-        const Real fx = rec.nx * ps_, fy = rec.ny * ps_;
-        if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; } else { tx += ex; ty += ey; qx += fx; qy += fy; }
-        if constexpr (sizeof(Real) == 4) { const R2 vj = vel[rec.j]; sum_vx += vj.x; sum_vy += vj.y; }
+    // batches of 4 pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
+    // latency bound (two dependent L2 round trips per pair), so the loads of a batch are issued back to back
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        uint32_t jj[4];
+        R2 nn[4];
+        PS<Real> pp[4];
+        R2 vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k0 + u < K) { jj[u] = pair_j[(size_t)off + k0 + u]; nn[u] = pair_n[(size_t)off + k0 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k0 + u < K) {
+                pp[u] = ps_in[jj[u]];
+                if constexpr (sizeof(Real) == 4) vv[u] = vel[jj[u]];
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (k0 + u < K) {
+                const R2 nv = nn[u];
+                const PS<Real> nb = pp[u];
+                // F3 pass 2, crate.py:347-353
+                const Real ddx = me.sx - nb.sx, ddy = me.sy - nb.sy;
+                const Real align = (ddx * nv.x + ddy * nv.y) * smooth;
+                const Real fix = nb.p + p_i - two_target;
+                const Real cc = align + fix;
+                const Real ex = cc * nv.x, ey = cc * nv.y;
+                // F5, crate.py:301-306
+                const Real ps_ = p_i + nb.p;
+                const Real fx = nv.x * ps_, fy = nv.y * ps_;
+                if (k0 + u == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
+                else { tx += ex; ty += ey; qx += fx; qy += fy; }
+                if constexpr (sizeof(Real) == 4) { sum_vx += vv[u].x; sum_vy += vv[u].y; }
+            }
     }
 
     // walls: contacts are recomputed from the position the particle had BEFORE apply_hard_wall_fix
@@ -357,7 +367,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         Real ax = 0, ay = 0;
         if constexpr (sizeof(Real) == 8) {
             for (int q = 0; q < K; ++q) {
-                const R2 vj = vel[mine[q].j];
+                const R2 vj = vel[pair_j[(size_t)off + q]];
                 const Real ex = vj.x - vx, ey = vj.y - vy;
                 if (q == 0) { ax = ex; ay = ey; } else { ax += ex; ay += ey; }
             }

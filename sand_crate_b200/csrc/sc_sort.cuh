@@ -161,8 +161,9 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
               const uint32_t *__restrict__ cell_key, const double2 *__restrict__ pos,
               const typename Vec2<Real>::type *__restrict__ vel, const uint32_t *__restrict__ uid,
               const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
-              double2 *__restrict__ pos_s, typename Vec2<Real>::type *__restrict__ vel_s,
-              uint32_t *__restrict__ uid_s, uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
+              double2 *__restrict__ pos_s, float2 *__restrict__ rel_s,
+              typename Vec2<Real>::type *__restrict__ vel_s, uint32_t *__restrict__ uid_s,
+              uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
               uint32_t *__restrict__ wall_slot_s) {
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,6 +183,13 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
     }
     const uint32_t f = beg + rank;
     pos_s[f] = p;
+    {   // cell-relative fp32 copy for the pair kernels' screening (see collect_neighbors)
+        const uint32_t cr = c / (uint32_t)g.ncols, cc = c - cr * (uint32_t)g.ncols;
+        float2 r;
+        r.x = (float)(p.x - (double)((int)cc + g.col_min) * g.d);
+        r.y = (float)(p.y - (double)((int)cr + g.row_min) * g.d);
+        rel_s[f] = r;
+    }
     vel_s[f] = vel[i];
     uid_s[f] = u;
     cell_key_s[f] = c;
@@ -203,18 +211,18 @@ k_mark_alive(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ ui
 // neighbor counts (and optionally lists, as sorted indices) - the parity tap and the SC_NOISE_HOST split step
 __global__ void __launch_bounds__(SC_BLOCK)
 k_count_neighbors(Counters *__restrict__ cnt, Grid g, const uint32_t *__restrict__ cell_start,
-                  const double2 *__restrict__ pos, const uint32_t *__restrict__ cell_key,
-                  const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
-                  uint32_t *__restrict__ count_by_rank, uint32_t *__restrict__ list_sorted) {
+                  const double2 *__restrict__ pos, const float2 *__restrict__ rel,
+                  const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ uid,
+                  const uint32_t *__restrict__ rank_of_uid, uint32_t *__restrict__ count_by_rank,
+                  uint32_t *__restrict__ list_sorted) {
     const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
-    const double2 ps = pos[s];
     __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
     NbrList lst{s_list + threadIdx.x};
-    const int K = collect_neighbors(s, ps, cell_key[s], g, cell_start, pos, lst);
+    const int K = collect_neighbors(s, cell_key[s], g, cell_start, rel, pos, lst);
     if (list_sorted)
-        for (int k = 0; k < K; ++k) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = lst.get(k);
+        for (int k = 0; k < K; ++k) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = lst.get(k) & SC_IDX_MASK;
     count_by_rank[rank_of_uid[uid[s]]] = (uint32_t)K;
     atomicAdd(&cnt->n_pairs, (uint32_t)K);
 }
@@ -238,6 +246,19 @@ k_scatter_scalar(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict_
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     dst[rank_of_uid[uid[s]]] = (double)src[s];
+}
+// pressure / surface normal out of the packed PS records
+template <typename Real>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_scatter_ps(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
+             const uint32_t *__restrict__ rank_of_uid, const PS<Real> *__restrict__ src, double *__restrict__ prs,
+             double2 *__restrict__ tens) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    const PS<Real> v = src[s];
+    const uint32_t r = rank_of_uid[uid[s]];
+    if (prs) prs[r] = (double)v.p;
+    if (tens) { double2 o; o.x = (double)v.sx; o.y = (double)v.sy; tens[r] = o; }
 }
 __global__ void __launch_bounds__(SC_BLOCK)
 k_scatter_uid(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
