@@ -44,7 +44,7 @@ struct sc_ctx {
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
     uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
     uint32_t *cell_start = nullptr; size_t cell_cap = 0;
-    uint32_t *bsum = nullptr; size_t bsum_cap = 0;
+    unsigned long long *bsum = nullptr; size_t bsum_cap = 0;  // scan tile descriptors; [bsum_cap - 1] = ticket
     void *ps = nullptr;               // PS<Real>[cap]: pressure + surface normal of the sorted set
     uint32_t *pair_j = nullptr; void *pair_n = nullptr;  // [cap * SC_MAX_NEIGHBORS], written by K4, read by K5
     uint32_t *pair_off = nullptr; uint8_t *pair_cnt = nullptr;
@@ -150,8 +150,8 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
         CKR(dev_alloc(ctx, &ctx->cell_start, need));
         ctx->cell_cap = need;
     }
-    const size_t nb = (size_t)(g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
-    const size_t nb2 = (size_t)(ctx->cap + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
+    const size_t nb = (size_t)(g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
+    const size_t nb2 = (size_t)(ctx->cap + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
     const size_t needb = nb > nb2 ? nb : nb2;
     if (needb > ctx->bsum_cap) {
         if (ctx->bsum) CK(cudaFree(ctx->bsum));
@@ -437,20 +437,20 @@ extern "C" int sc_particle_count(sc_ctx *ctx, int64_t *n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot) {
+// In-place exclusive scan of a[0..n), total to a[n].  `pre_cleared`: the descriptors were zeroed by k_begin_tick.
+static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot, bool pre_cleared = false) {
     const unsigned nb = (n + SC_SCAN_TILE - 1) / SC_SCAN_TILE;
     if (nb == 0) { CK(cudaMemsetAsync(a, 0, sizeof(uint32_t), ctx->stream)); return 0; }
-    if (nb + 1 > ctx->bsum_cap) {
+    if ((size_t)nb + 2 > ctx->bsum_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->bsum) CK(cudaFree(ctx->bsum));
-        CKR(dev_alloc(ctx, &ctx->bsum, (size_t)nb + 1));
-        ctx->bsum_cap = (size_t)nb + 1;
+        CKR(dev_alloc(ctx, &ctx->bsum, (size_t)nb + 2));
+        ctx->bsum_cap = (size_t)nb + 2;
+        pre_cleared = false;
     }
+    if (!pre_cleared) CK(cudaMemsetAsync(ctx->bsum, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
     ProfScope ps(ctx, slot);
-    k_scan_reduce<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum);
-    k_scan_sums<<<1, SC_BLOCK, 0, ctx->stream>>>(ctx->bsum, nb);
-    k_scan_apply<<<nb, SC_BLOCK, 0, ctx->stream>>>(a, n, ctx->bsum);
-    ctx->launches += 2;
+    k_scan_lookback<<<nb, SC_SCAN_THREADS, 0, ctx->stream>>>(a, n, ctx->bsum + 1, (uint32_t *)ctx->bsum);
     return 0;
 }
 
@@ -490,21 +490,23 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         ProfScope ps(ctx, SLOT_CLEAR);
         const uint32_t words = (uint32_t)(n / 32 + 1);
         const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
+        const uint32_t scan_words = (g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;  // ticket + descriptors
         k_begin_tick<<<nb, SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start, g.ncells, ctx->carry_count ? 1 : 0,
-                                                       ctx->wall_bits_cur, ctx->wall_bits_srt, words);
+                                                       ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum,
+                                                       scan_words);
         ctx->carry_count = false;
     }
     if (n > 0) {
         ProfScope ps(ctx, SLOT_PREPASS);
-        k_prepass<kStep><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+        k_prepass<kStep><<<blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP), SC_BLOCK, 0, ctx->stream>>>(
             ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot, ctx->cell_start,
             ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre);
     }
-    CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN));
+    CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
         {
             ProfScope ps(ctx, SLOT_PLACE);
-            k_place<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_key, ctx->slot, ctx->cell_start,
+            k_place<<<blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP), SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_key, ctx->slot, ctx->cell_start,
                                                                  ctx->tmpidx);
         }
         ProfScope ps(ctx, SLOT_RANK_GATHER);

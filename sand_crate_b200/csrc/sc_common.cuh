@@ -134,9 +134,10 @@ __device__ inline uint32_t cell_of(const Grid &g, double x, double y, int &row_o
 // original index order == uid order)
 __device__ inline bool x_less(double a, double b) { return a < b || (b != b && a == a); }
 
-// exclusive prefix sum over the SC_BLOCK threads of a block; `total` = sum over the block
-__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
-    __shared__ uint32_t warp_sums[SC_BLOCK / 32];
+// exclusive prefix sum over the NT threads of a block; `total` = sum over the block
+template <int NT>
+__device__ inline uint32_t block_exclusive_scan_n(uint32_t v, uint32_t &total) {
+    __shared__ uint32_t warp_sums[NT / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -147,19 +148,22 @@ __device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
     if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < SC_BLOCK / 32 ? warp_sums[lane] : 0;
+        uint32_t w = lane < NT / 32 ? warp_sums[lane] : 0;
 #pragma unroll
-        for (int o = 1; o < SC_BLOCK / 32; o <<= 1) {
+        for (int o = 1; o < NT / 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
             if (lane >= o) w += t;
         }
-        if (lane < SC_BLOCK / 32) warp_sums[lane] = w;
+        if (lane < NT / 32) warp_sums[lane] = w;
     }
     __syncthreads();
     const uint32_t base = wid ? warp_sums[wid - 1] : 0;
-    total = warp_sums[SC_BLOCK / 32 - 1];
+    total = warp_sums[NT / 32 - 1];
     __syncthreads();
     return base + inc - v;
+}
+__device__ inline uint32_t block_exclusive_scan(uint32_t v, uint32_t &total) {
+    return block_exclusive_scan_n<SC_BLOCK>(v, total);
 }
 
 }  // namespace sc

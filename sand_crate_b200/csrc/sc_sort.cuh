@@ -13,62 +13,88 @@ namespace sc {
 //   kStep = true : remove_particles (crate.py:149-159), calc_virtual_colliders + apply_hard_wall_fix
 //                  (crate.py:213-243, 202-211), then the cell key
 //   kStep = false: cell key only (standalone detect_particle_collisions)
+#define SC_PREPASS_ILP 2  // particles per thread: the kernel is a chain of two long-latency operations (position
+                          // load, histogram atomic), so independent chains are interleaved
 template <bool kStep>
-__global__ void __launch_bounds__(SC_BLOCK)
+__global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it is rare
 k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
           double2 *__restrict__ pos, uint32_t *__restrict__ cell_key, uint32_t *__restrict__ slot,
           uint32_t *__restrict__ cell_count, uint32_t *__restrict__ wall_bits, uint32_t *__restrict__ wall_slot,
           double2 *__restrict__ wall_pre) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cnt->n) return;
-    double2 p = pos[i];
-    if (kStep) {
-        const bool out = (p.x < P.box_lo) | (p.x > P.box_hi) | (p.y < P.box_lo) | (p.y > P.box_hi);
-        if (out) {
-            cell_key[i] = SC_INVALID_CELL;
-            atomicAdd(&cnt->n_removed, 1u);
-            return;
-        }
-        int V = 0;
-        double sx = 0, sy = 0;
-        // one test for the bulk of the liquid: inside a rectangle that no segment's touch zone reaches
-        const bool clear = p.x > W.safe_contact[0] && p.x < W.safe_contact[1] && p.y > W.safe_contact[2] &&
-                           p.y < W.safe_contact[3];
-        for (int q = 0; !clear && q < W.S; ++q) {
-            if (p.x < W.seg_box[q][0] || p.x > W.seg_box[q][1] || p.y < W.seg_box[q][2] || p.y > W.seg_box[q][3])
-                continue;  // cannot be within the touch distance of this segment
-            double cx, cy;
-            const double dist = point_segment(p.x, p.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy);
-            if (dist <= P.touch) {
-                const double vcx = (p.x - cx) * 2, vcy = (p.y - cy) * 2;  // crate.py:234
-                double rel = P.r / sqrt(vcx * vcx + vcy * vcy);            // crate.py:206
-                if (rel < 0.5) rel = 0.5;
-                const double ex = vcx * (rel - 0.5), ey = vcy * (rel - 0.5);
-                if (V == 0) { sx = ex; sy = ey; } else { sx += ex; sy += ey; }
-                ++V;
+    const uint32_t n = cnt->n;
+    const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
+    double2 p[SC_PREPASS_ILP];
+    uint32_t c[SC_PREPASS_ILP];
+#pragma unroll
+    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
+        const uint32_t i = i0 + u * SC_BLOCK;
+        if (i < n) p[u] = pos[i];
+    }
+#pragma unroll
+    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
+        const uint32_t i = i0 + u * SC_BLOCK;
+        c[u] = SC_INVALID_CELL;
+        if (i >= n) continue;
+        if (kStep) {
+            const bool out = (p[u].x < P.box_lo) | (p[u].x > P.box_hi) | (p[u].y < P.box_lo) | (p[u].y > P.box_hi);
+            if (out) {
+                cell_key[i] = SC_INVALID_CELL;
+                atomicAdd(&cnt->n_removed, 1u);
+                continue;
+            }
+            // one test for the bulk of the liquid: inside a rectangle that no segment's touch zone reaches
+            const bool clear = p[u].x > W.safe_contact[0] && p[u].x < W.safe_contact[1] &&
+                               p[u].y > W.safe_contact[2] && p[u].y < W.safe_contact[3];
+            if (!clear) {
+                int V = 0;
+                double sx = 0, sy = 0;
+                for (int q = 0; q < W.S; ++q) {
+                    if (p[u].x < W.seg_box[q][0] || p[u].x > W.seg_box[q][1] || p[u].y < W.seg_box[q][2] ||
+                        p[u].y > W.seg_box[q][3])
+                        continue;  // cannot be within the touch distance of this segment
+                    double cx, cy;
+                    const double dist = point_segment(p[u].x, p[u].y, W.seg[q][0], W.seg[q][1], W.seg[q][2],
+                                                      W.seg[q][3], cx, cy);
+                    if (dist <= P.touch) {
+                        const double vcx = (p[u].x - cx) * 2, vcy = (p[u].y - cy) * 2;  // crate.py:234
+                        double rel = P.r / sqrt(vcx * vcx + vcy * vcy);                  // crate.py:206
+                        if (rel < 0.5) rel = 0.5;
+                        const double ex = vcx * (rel - 0.5), ey = vcy * (rel - 0.5);
+                        if (V == 0) { sx = ex; sy = ey; } else { sx += ex; sy += ey; }
+                        ++V;
+                    }
+                }
+                if (V > 0) {
+                    const uint32_t ws = atomicAdd(&cnt->n_wall, 1u);
+                    wall_pre[ws] = p[u];  // contacts are re-derived from this position by the force kernel
+                    wall_slot[i] = ws;
+                    atomicOr(&wall_bits[i >> 5], 1u << (i & 31));
+                    p[u].x += sx;
+                    p[u].y += sy;
+                    pos[i] = p[u];
+                }
             }
         }
-        if (V > 0) {
-            const uint32_t ws = atomicAdd(&cnt->n_wall, 1u);
-            wall_pre[ws] = p;  // contacts are re-derived from this position by the force kernel
-            wall_slot[i] = ws;
-            atomicOr(&wall_bits[i >> 5], 1u << (i & 31));
-            p.x += sx;
-            p.y += sy;
-            pos[i] = p;
-        }
+        int row;
+        c[u] = cell_of(g, p[u].x, p[u].y, row);
     }
-    int row;
-    const uint32_t c = cell_of(g, p.x, p.y, row);
-    cell_key[i] = c;
-    slot[i] = atomicAdd(&cell_count[c], 1u);
+    uint32_t sl[SC_PREPASS_ILP];
+#pragma unroll
+    for (int u = 0; u < SC_PREPASS_ILP; ++u)
+        if (c[u] != SC_INVALID_CELL) sl[u] = atomicAdd(&cell_count[c[u]], 1u);
+#pragma unroll
+    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
+        const uint32_t i = i0 + u * SC_BLOCK;
+        if (c[u] != SC_INVALID_CELL) { cell_key[i] = c[u]; slot[i] = sl[u]; }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply).
 // 16 items per thread as four 128-bit accesses: a warp request covers 2 KB contiguous.
 #define SC_SCAN_ITEMS 16
-#define SC_SCAN_TILE (SC_BLOCK * SC_SCAN_ITEMS)
+#define SC_SCAN_THREADS 1024  // few, large tiles: the look-back of tile k walks k / 32 windows when all start together
+#define SC_SCAN_TILE (SC_SCAN_THREADS * SC_SCAN_ITEMS)
 
 __device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {
     if (base + SC_SCAN_ITEMS <= n) {
@@ -84,44 +110,61 @@ __device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32
     }
 }
 
-__global__ void __launch_bounds__(SC_BLOCK) k_scan_reduce(const uint32_t *__restrict__ a, uint32_t n,
-                                                         uint32_t *__restrict__ bsum) {
-    const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
+// Single-pass exclusive scan (decoupled look-back): one launch, 8 bytes of traffic per item.  Tiles take their index
+// from a ticket counter, so a tile's predecessors are always resident or done and the look-back cannot deadlock.
+// Tile descriptor = (status << 32) | value, written / read as one 64-bit word: status 1 = tile aggregate,
+// 2 = inclusive prefix.  `desc` (one word per tile) and `ticket` must be zero at launch.
+__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(SC_SCAN_THREADS)
+k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__restrict__ desc,
+                uint32_t *__restrict__ ticket) {
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
     uint32_t item[SC_SCAN_ITEMS];
     scan_load(a, n, base, item);
     uint32_t v = 0;
 #pragma unroll
     for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
     uint32_t total;
-    block_exclusive_scan(v, total);
-    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SC_BLOCK) k_scan_sums(uint32_t *__restrict__ bsum, uint32_t nb) {
-    // single block: each thread scans a contiguous chunk
-    const uint32_t per = (nb + SC_BLOCK - 1) / SC_BLOCK;
-    const uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, nb);
-    uint32_t v = 0;
-    for (uint32_t q = b0; q < b1; ++q) v += bsum[q];
-    uint32_t total;
-    uint32_t run = block_exclusive_scan(v, total);
-    for (uint32_t q = b0; q < b1; ++q) {
-        const uint32_t t = bsum[q];
-        bsum[q] = run;
-        run += t;
+    const uint32_t before = block_exclusive_scan_n<SC_SCAN_THREADS>(v, total);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0) st_desc(desc + tile, ((tile == 0 ? 2ull : 1ull) << 32) | total);
+        uint32_t exclusive = 0;
+        int look = (int)tile - 1;
+        while (look >= 0) {  // warp-wide window over the 32 nearest predecessors
+            const int idx = look - lane;
+            unsigned long long d;
+            do {
+                d = idx >= 0 ? ld_desc(desc + idx) : (2ull << 32);
+            } while (__any_sync(0xffffffffu, (d >> 32) == 0ull));
+            const unsigned has_prefix = __ballot_sync(0xffffffffu, (d >> 32) == 2ull);
+            const int first = has_prefix ? __ffs((int)has_prefix) - 1 : 31;  // nearest tile with a full prefix
+            uint32_t val = lane <= first ? (uint32_t)d : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            exclusive += val;
+            if (has_prefix) break;
+            look -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) st_desc(desc + tile, (2ull << 32) | (unsigned long long)(exclusive + total));
+            s_prefix = exclusive;
+        }
     }
-}
-
-__global__ void __launch_bounds__(SC_BLOCK) k_scan_apply(uint32_t *__restrict__ a, uint32_t n,
-                                                        const uint32_t *__restrict__ bsum) {
-    const uint32_t base = blockIdx.x * SC_SCAN_TILE + threadIdx.x * SC_SCAN_ITEMS;
-    uint32_t item[SC_SCAN_ITEMS];
-    scan_load(a, n, base, item);
-    uint32_t v = 0;
-#pragma unroll
-    for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
-    uint32_t total;
-    uint32_t run = block_exclusive_scan(v, total) + bsum[blockIdx.x];
+    __syncthreads();
+    uint32_t run = s_prefix + before;
 #pragma unroll
     for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
         const uint32_t t = item[q];
@@ -137,20 +180,31 @@ __global__ void __launch_bounds__(SC_BLOCK) k_scan_apply(uint32_t *__restrict__ 
         for (int q = 0; q < SC_SCAN_ITEMS; ++q)
             if (base + q < n) a[base + q] = item[q];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SC_BLOCK - 1) a[n] = run;  // grand total
+    if (tile == gridDim.x - 1 && threadIdx.x == SC_SCAN_THREADS - 1) a[n] = run;  // grand total
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // K2: counting-sort placement.  The arrival slot inside a cell came from an atomic, so the order inside a cell
 // is arbitrary here; k_rank_gather makes it deterministic.
+#define SC_PLACE_ILP 4
 __global__ void __launch_bounds__(SC_BLOCK)
 k_place(const Counters *__restrict__ cnt, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ slot,
         const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ tmpidx) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= cnt->n) return;
-    const uint32_t c = cell_key[i];
-    if (c == SC_INVALID_CELL) return;
-    tmpidx[cell_start[c] + slot[i]] = i;
+    const uint32_t n = cnt->n;
+    const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
+    uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP];
+#pragma unroll
+    for (int u = 0; u < SC_PLACE_ILP; ++u) {
+        const uint32_t i = i0 + u * SC_BLOCK;
+        c[u] = SC_INVALID_CELL;
+        if (i < n) { c[u] = cell_key[i]; sl[u] = slot[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < SC_PLACE_ILP; ++u)
+        if (c[u] != SC_INVALID_CELL) st[u] = cell_start[c[u]];
+#pragma unroll
+    for (int u = 0; u < SC_PLACE_ILP; ++u)
+        if (c[u] != SC_INVALID_CELL) tmpidx[st[u] + sl[u]] = i0 + u * SC_BLOCK;
 }
 
 // K3: rank inside the cell by (x, uid) and gather the particle record to its final sorted position.
@@ -346,7 +400,8 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
 // bitmaps.  Entry [ncells] (the previous total) is deliberately not zeroed: the scan rewrites it.
 __global__ void __launch_bounds__(SC_BLOCK)
 k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, int carry_count,
-             uint32_t *__restrict__ bits_a, uint32_t *__restrict__ bits_b, uint32_t nbits_words) {
+             uint32_t *__restrict__ bits_a, uint32_t *__restrict__ bits_b, uint32_t nbits_words,
+             unsigned long long *__restrict__ scan_desc, uint32_t scan_words) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
@@ -357,6 +412,7 @@ k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, 
     for (uint32_t i = tid; i < n4; i += nth) c4[i] = make_uint4(0, 0, 0, 0);
     for (uint32_t i = n4 * 4 + tid; i < ncells; i += nth) cell_count[i] = 0;
     for (uint32_t i = tid; i < nbits_words; i += nth) { bits_a[i] = 0; bits_b[i] = 0; }
+    for (uint32_t i = tid; i < scan_words; i += nth) scan_desc[i] = 0ull;  // tile descriptors + ticket of the cell scan
 }
 
 template <typename Real>
