@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--scene", default="dam_break", choices=["dam_break", "box_fill"])
     ap.add_argument("--particles", type=int, default=1_000_000)
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
+    ap.add_argument("--mgpu-particles", type=int, default=2_000_000, help="particles per GPU when --gpus > 1")
     ap.add_argument("--cpu-particles", type=int, default=200_000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,8 +211,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = a.particles
-    world, pos, vel = SCENES[a.scene](n, seed=42 + rank)
     # a non-default torch stream: the library launches on it and torch.cuda.Event records on it (handle 0, the
     # legacy default stream, would make sc_create open a private stream that torch events cannot see)
     tstream = torch.cuda.Stream()
@@ -219,15 +218,37 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
     precision = _lib.PRECISION_MIXED if a.precision == "mixed" else _lib.PRECISION_F64
-    ctx = _lib.Context(n, precision, local_rank, stream)
-    ctx.set_params(**scene_params(world))
-    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
-    ctx.set_walls(seg, [4], np.zeros((1, 5)))
-    ctx.set_noise(_lib.NOISE_COUNTER, 0)
-    ctx.set_state(pos, vel)
+    dom = None
+    if world_size == 1:
+        n = a.particles
+        scene = a.scene
+        world, pos, vel = SCENES[scene](n)
+        ctx = _lib.Context(n, precision, local_rank, stream)
+        ctx.set_params(**scene_params(world))
+        seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+        ctx.set_walls(seg, [4], np.zeros((1, 5)))
+        ctx.set_noise(_lib.NOISE_COUNTER, 0)
+        ctx.set_state(pos, vel)
+        step_fn = ctx.step
+        n_total = n
+    else:
+        # one scene cut into horizontal strips of cell rows, NCCL halo + migration exchange every tick
+        # (BASELINE.json configs[3]: box-fill, 2M particles per GPU = 16M on 8 GPUs)
+        from sand_crate_b200.strips import StripDomain
+        scene = "box_fill" if a.scene == "dam_break" and a.particles == 1_000_000 else a.scene
+        per_gpu = a.mgpu_particles if a.particles == 1_000_000 else a.particles
+        n_total = per_gpu * world_size
+        world, pos, vel = SCENES[scene](n_total)
+        dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
+                          device=local_rank, stream=stream)
+        ctx = dom.ctx
+        step_fn = dom.physics_tick
+        n = n_total // world_size
+        del pos, vel
 
     flush = None if a.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    ctx.step(a.warmup)
+    for _ in range(a.warmup):
+        step_fn()
     barrier()
 
     def timed_pass(profile):
@@ -240,7 +261,7 @@ def main():
             if flush is not None:
                 flush.fill_(1)          # untimed: evicts the previous step's lines from the 126 MB L2
             e0.record()
-            ctx.step()
+            step_fn()
             e1.record()
         barrier()
         w = time.perf_counter() - w0
@@ -259,37 +280,57 @@ def main():
     # the roofline); the extra event records stretch the gaps between kernels, so its step time is not the headline
     total_ms_prof, _, kernels = timed_pass(True)
     clocks = sampler.stop()
-    n_live = ctx.particle_count()
+    n_live = ctx.particle_count() if dom is None else dom.status()["n_local"]
+    dist_status = None if dom is None else dom.status()
 
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    value = world_size * n * a.steps / (total_ms_max * 1e-3)
+    value = n_total * a.steps / (total_ms_max * 1e-3)
 
     # ---- e2e: the public API with host buffers: upload state, tick, read the result back, every step ----------
-    crate = Crate(world, precision=a.precision, noise="counter", device=local_rank, capacity=n, stream=stream)
-    hp = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
-    hv = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
-    gp, gv, _ = ctx.get_state(want_pressure=False)
-    hp[:], hv[:] = gp, gv
+    if dom is None:
+        crate = Crate(world, precision=a.precision, noise="counter", device=local_rank, capacity=n, stream=stream)
+        hp = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
+        hv = torch.empty((n, 2), dtype=torch.float64, pin_memory=True).numpy()
+        gp, gv, _ = ctx.get_state(want_pressure=False)
+        hp[:], hv[:] = gp, gv
+
+        def e2e_step():
+            crate.set_particles(hp, hv)
+            crate.physics_tick()
+            return crate._ctx.get_state(want_vel=False, want_pressure=False)[0]
+        e2e_api = "Crate.set_particles(host) -> physics_tick() -> particles (host)"
+    else:
+        uid0, gp, gv = dom.owned()
+        m = len(uid0)
+        hp = torch.empty((m, 2), dtype=torch.float64, pin_memory=True).numpy()
+        hv = torch.empty((m, 2), dtype=torch.float64, pin_memory=True).numpy()
+        hp[:], hv[:] = gp, gv
+
+        def e2e_step():
+            dom.ctx.set_state_uids(hp, hv, uid0)
+            dom.physics_tick()
+            return dom.ctx.dist_get_owned()[0]
+        e2e_api = "Context.set_state_uids(host) -> StripDomain.physics_tick() -> dist_get_owned (host), per rank"
     for _ in range(3):
-        crate.set_particles(hp, hv)
-        crate.physics_tick()
-        _ = crate.particles
+        out_pos = e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(a.e2e_steps):
-        crate.set_particles(hp, hv)
-        crate.physics_tick()
-        out_pos = crate._ctx.get_state(want_vel=False, want_pressure=False)[0]
+        out_pos = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world_size * n * a.e2e_steps / float(t.item())
+    e2e_value = n_total * a.e2e_steps / float(t.item())
     assert np.isfinite(out_pos).all()
+    h2d = torch.tensor([float(hp.nbytes + hv.nbytes), float(out_pos.nbytes)], device="cuda", dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(h2d)
+    h2d_bytes, d2h_bytes = int(h2d[0].item()), int(h2d[1].item())
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -311,15 +352,18 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 forces / f64 positions" if a.precision == "mixed" else "f64", "data": "synthetic",
-            "config": {"workload": f"{a.scene} {n} particles per GPU, closed unit box, counter noise 0.1",
-                       "scene": a.scene, "particles_per_gpu": n, "live_particles_rank0": n_live,
-                       "parallelism": "single GPU" if world_size == 1 else f"{world_size} independent replicas",
+            "config": {"workload": f"{scene} {n_total} particles ({n} per GPU), closed unit box, counter noise 0.1",
+                       "scene": scene, "particles_total": n_total, "particles_per_gpu": n,
+                       "local_particles_rank0": n_live,
+                       "parallelism": "single GPU" if world_size == 1 else
+                       f"{world_size} horizontal strips of cell rows, NCCL send/recv halo + migration with rank+-1 "
+                       f"every tick (halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records)",
+                       "dist_status_rank0": dist_status,
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hp.nbytes + hv.nbytes),
-                    "d2h_bytes_per_step": int(out_pos.nbytes), "steps": a.e2e_steps,
-                    "api": "Crate.set_particles(host) -> physics_tick() -> particles (host)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": a.e2e_steps, "api": e2e_api},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

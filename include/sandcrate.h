@@ -129,6 +129,33 @@ int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int slots);
 const char *sc_profile_name(int slot);
 int64_t sc_launch_count(const sc_ctx *ctx); /* kernels launched by this context so far */
 
+/* ---- multi-GPU strip decomposition (one context per rank; the transport is the caller's: NCCL send/recv) ------ */
+/* The reference's search is already a 1-D strip decomposition in y with strip height one diameter
+ * (collision_detector.py:10-31, 124-128); rank k owns the cell rows row_lo <= floor(y / d) < row_hi.  Every tick,
+ * before sc_step:
+ *   sc_dist_pack    drops last tick's ghosts, turns particles whose row left the strip into MIGRANT records for the
+ *                   neighbor (they stay here as ghosts for this tick) and copies owned particles within `halo_rows`
+ *                   of a cut into HALO records;  send_*_dev: device buffers of sc_dist_wire_bytes(capacity) bytes
+ *                   (16-byte header with the record count, then 40-byte records), NULL where there is no neighbor
+ *   (caller)        exchanges the buffers, whole, with rank - 1 / rank + 1
+ *   sc_dist_unpack  appends received migrants as owned particles and received halos as ghosts
+ * A ghost is simulated like any particle and discarded by the next pack.  With halo_rows >= 4 every owned particle
+ * sees the neighbors, pressures and normals of the global computation in the same order: SC_PRECISION_F64 results
+ * are bit-identical to a single-GPU run.  Noise must be SC_NOISE_COUNTER or SC_NOISE_NONE.  uids must be < 2^31. */
+int64_t sc_dist_wire_bytes(int64_t wire_capacity);
+int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t row_hi, int halo_rows,
+                      int64_t wire_capacity);
+int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev);
+int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev);
+/* owned particles of this rank, in arbitrary order; uid[i] identifies row i.  Synchronises. */
+int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int64_t cap, int64_t *n);
+/* device-side flags since creation: capacity overflow, a particle that crossed a whole halo in one tick; the
+ * number of local particles (owned + ghosts).  Synchronises. */
+int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *send_hi_dev, int *overflow, int *too_far,
+                   int64_t *n_local);
+/* like sc_set_state but with caller-chosen uids (global particle ids of a partitioned scene) */
+int sc_set_state_uids(sc_ctx *ctx, const double *pos, const double *vel, const uint32_t *uid, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,13 @@ SIGNATURES = {
     "sc_detect_particle_collisions": (C.c_int, [_ctx, _dp, C.c_int64, C.c_double, _lp, _lp, _ip, _ip]),
     "sc_points_to_segments_distance": (C.c_int, [_ctx, _dp, C.c_int64, _dp, C.c_int, _dp, _dp]),
     "sc_pad_segments": (C.c_int, [_dp, C.c_int, C.c_double, _dp]),
+    "sc_dist_wire_bytes": (C.c_int64, [C.c_int64]),
+    "sc_dist_configure": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64]),
+    "sc_dist_pack": (C.c_int, [_ctx, C.c_void_p, C.c_void_p]),
+    "sc_dist_unpack": (C.c_int, [_ctx, C.c_void_p, C.c_void_p]),
+    "sc_dist_get_owned": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64, _lp]),
+    "sc_dist_status": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
+    "sc_set_state_uids": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64]),
     "sc_profile_enable": (C.c_int, [_ctx, C.c_int]),
     "sc_profile_read": (C.c_int, [_ctx, _lp, _dp, C.c_int]),
     "sc_profile_name": (C.c_char_p, [C.c_int]),
@@ -251,6 +258,43 @@ class Context:
                                                         _ptr(near, _dp), _ptr(dist, _dp)))
         return near, dist
 
+    # ---- strip decomposition (device pointers are plain ints, e.g. torch.Tensor.data_ptr()) ----
+    def set_state_uids(self, pos, vel, uid):
+        pos, vel = _f64(pos, 2), _f64(vel, 2)
+        uid = np.ascontiguousarray(uid, dtype=np.uint32)
+        assert pos.shape == vel.shape and uid.shape[0] == pos.shape[0]
+        self._ck(self._L.sc_set_state_uids(self._h, _ptr(pos, _dp), _ptr(vel, _dp), _ptr(uid, _up), pos.shape[0]))
+
+    def dist_configure(self, rank, nranks, row_lo, row_hi, halo_rows, wire_capacity):
+        self._ck(self._L.sc_dist_configure(self._h, int(rank), int(nranks), int(row_lo), int(row_hi), int(halo_rows),
+                                           int(wire_capacity)))
+
+    @staticmethod
+    def _devptr(buf):
+        """None, an integer device address, or anything with data_ptr() (a torch tensor on this GPU)."""
+        if buf is None:
+            return C.c_void_p(None)
+        return C.c_void_p(int(buf.data_ptr()) if hasattr(buf, "data_ptr") else int(buf))
+
+    def dist_pack(self, send_lo, send_hi):
+        self._ck(self._L.sc_dist_pack(self._h, self._devptr(send_lo), self._devptr(send_hi)))
+
+    def dist_unpack(self, recv_lo, recv_hi):
+        self._ck(self._L.sc_dist_unpack(self._h, self._devptr(recv_lo), self._devptr(recv_hi)))
+
+    def dist_get_owned(self):
+        cap = self.capacity
+        pos, vel, uid = np.empty((cap, 2)), np.empty((cap, 2)), np.empty(cap, np.uint32)
+        n = C.c_int64()
+        self._ck(self._L.sc_dist_get_owned(self._h, _ptr(pos, _dp), _ptr(vel, _dp), _ptr(uid, _up), cap, C.byref(n)))
+        return pos[:n.value].copy(), vel[:n.value].copy(), uid[:n.value].copy()
+
+    def dist_status(self, send_lo=None, send_hi=None):
+        ov, far, n = C.c_int(), C.c_int(), C.c_int64()
+        self._ck(self._L.sc_dist_status(self._h, self._devptr(send_lo), self._devptr(send_hi),
+                                        C.byref(ov), C.byref(far), C.byref(n)))
+        return {"overflow": bool(ov.value), "too_far": bool(far.value), "n_local": n.value}
+
     # ---- measurement ----
     def profile_enable(self, on: bool = True):
         self._ck(self._L.sc_profile_enable(self._h, int(on)))
@@ -268,6 +312,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.sc_launch_count(self._h))
+
+
+def wire_bytes(wire_capacity: int) -> int:
+    return int(load().sc_dist_wire_bytes(int(wire_capacity)))
 
 
 def pad_segments(segments, pad):

@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "sc_sort.cuh"
+#include "sc_dist.cuh"
 
 using namespace sc;
 
@@ -62,6 +62,9 @@ struct sc_ctx {
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
     bool lists_valid = false, rank_valid = false;
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
+    bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
+    DistCfg dist{};
+    WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers
     int64_t launches = 0;
     bool profiling = false;
     std::vector<ProfEvent> pending;
@@ -237,7 +240,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
                     c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
-                    c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1};
+                    c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : c->pool) cudaEventDestroy(e);
@@ -415,6 +418,20 @@ extern "C" int sc_set_state(sc_ctx *ctx, const double *pos, const double *vel, i
     CK(cudaMemcpyAsync(&ctx->cnt->n, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->n_host = 0; ctx->n_exact = true;
     return upload_particles(ctx, pos, vel, 0, n);
+}
+
+extern "C" int sc_set_state_uids(sc_ctx *ctx, const double *pos, const double *vel, const uint32_t *uid, int64_t n) {
+    if (!uid) return fail(ctx, "sc_set_state_uids: uid is NULL");
+    uint32_t top = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (uid[i] & SC_GHOST_BIT) return fail(ctx, "sc_set_state_uids: uids must be < 2^31");
+        if (uid[i] > top) top = uid[i];
+    }
+    CKR(sc_set_state(ctx, pos, vel, n));
+    if (n) CK(cudaMemcpyAsync(ctx->uid_cur, uid, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->next_uid = top + 1;
+    return 0;
 }
 
 extern "C" int sc_append_particles(sc_ctx *ctx, const double *pos, const double *vel, int64_t n) {
@@ -917,3 +934,154 @@ extern "C" int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int s
 }
 extern "C" const char *sc_profile_name(int slot) { return (slot >= 0 && slot < SC_PROFILE_SLOTS) ? k_slot_names[slot] : ""; }
 extern "C" int64_t sc_launch_count(const sc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+
+// ---- strip decomposition ------------------------------------------------------------------------------------
+static int dist_ready(sc_ctx *ctx, const char *who) {
+    CKR(require_ready(ctx, who));
+    if (!ctx->dist_on) return fail(ctx, std::string(who) + ": sc_dist_configure has not been called");
+    if (ctx->in_step) return fail(ctx, std::string(who) + ": inside a split step");
+    return 0;
+}
+
+extern "C" int64_t sc_dist_wire_bytes(int64_t wire_capacity) {
+    return (int64_t)sizeof(WireHeader) + (int64_t)sizeof(WireRec) * wire_capacity;
+}
+
+extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t row_hi, int halo_rows,
+                                 int64_t wire_capacity) {
+    if (!ctx) return fail(ctx, "sc_dist_configure: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, "sc_dist_configure: bad rank");
+    if (halo_rows < 1) return fail(ctx, "sc_dist_configure: halo_rows must be >= 1");
+    if (wire_capacity < 1 || wire_capacity > ctx->cap) return fail(ctx, "sc_dist_configure: bad wire capacity");
+    if (rank > 0 && rank < nranks - 1 && row_hi - row_lo < 2 * (int64_t)halo_rows)
+        return fail(ctx, "sc_dist_configure: a strip must be at least 2 * halo_rows high");
+    if (ctx->noise_mode == SC_NOISE_HOST) return fail(ctx, "sc_dist_configure: SC_NOISE_HOST is single-GPU only");
+    ctx->dist.row_lo = row_lo; ctx->dist.row_hi = row_hi; ctx->dist.halo = halo_rows;
+    ctx->dist.has_lo = rank > 0; ctx->dist.has_hi = rank < nranks - 1;
+    ctx->dist.cap = (uint32_t)wire_capacity;
+    if (!ctx->wire_dummy) CKR(dev_alloc(ctx, &ctx->wire_dummy, 2));
+    ctx->dist_on = true;
+    return 0;
+}
+
+__global__ void k_set_count(Counters *cnt) { cnt->n = cnt->n_tmp; }
+
+extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
+    CKR(dist_ready(ctx, "sc_dist_pack"));
+    if ((ctx->dist.has_lo && !send_lo_dev) || (ctx->dist.has_hi && !send_hi_dev))
+        return fail(ctx, "sc_dist_pack: a neighbor exists but its send buffer is NULL");
+    if (ctx->carry_count) {
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
+        ctx->carry_count = false;
+    }
+    WireHeader *lo = send_lo_dev ? (WireHeader *)send_lo_dev : ctx->wire_dummy;
+    WireHeader *hi = send_hi_dev ? (WireHeader *)send_hi_dev : ctx->wire_dummy + 1;
+    const int64_t n = ctx->n_host;
+    {
+        ProfScope ps(ctx, SLOT_IO);
+        k_wire_reset<<<1, 1, 0, ctx->stream>>>(lo, hi, &ctx->cnt->n_tmp);
+    }
+    if (n > 0) {
+        ProfScope ps(ctx, SLOT_IO);
+        if (ctx->precision == SC_PRECISION_F64)
+            k_dist_pack<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                ctx->cnt, &ctx->cnt->n, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur,
+                ctx->pos_srt, (double2 *)ctx->vel_srt, ctx->uid_srt, &ctx->cnt->n_tmp, (uint32_t)ctx->cap, lo, hi);
+        else
+            k_dist_pack<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                ctx->cnt, &ctx->cnt->n, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur,
+                ctx->pos_srt, (float2 *)ctx->vel_srt, ctx->uid_srt, &ctx->cnt->n_tmp, (uint32_t)ctx->cap, lo, hi);
+    }
+    {
+        ProfScope ps(ctx, SLOT_IO);
+        k_set_count<<<1, 1, 0, ctx->stream>>>(ctx->cnt);
+    }
+    CK(cudaGetLastError());
+    std::swap(ctx->pos_cur, ctx->pos_srt);
+    std::swap(ctx->vel_cur, ctx->vel_srt);
+    std::swap(ctx->uid_cur, ctx->uid_srt);
+    ctx->srt_valid = false; ctx->rank_valid = false; ctx->lists_valid = false;
+    ctx->n_exact = false;
+    return 0;
+}
+
+extern "C" int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev) {
+    CKR(dist_ready(ctx, "sc_dist_unpack"));
+    const void *bufs[2] = {ctx->dist.has_lo ? recv_lo_dev : nullptr, ctx->dist.has_hi ? recv_hi_dev : nullptr};
+    for (int q = 0; q < 2; ++q) {
+        if (!bufs[q]) continue;
+        ProfScope ps(ctx, SLOT_IO);
+        if (ctx->precision == SC_PRECISION_F64)
+            k_dist_unpack<double><<<blocks_for(ctx->dist.cap), SC_BLOCK, 0, ctx->stream>>>(
+                (const WireHeader *)bufs[q], ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur,
+                &ctx->cnt->n, (uint32_t)ctx->cap, &ctx->cnt->overflow);
+        else
+            k_dist_unpack<float><<<blocks_for(ctx->dist.cap), SC_BLOCK, 0, ctx->stream>>>(
+                (const WireHeader *)bufs[q], ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur,
+                &ctx->cnt->n, (uint32_t)ctx->cap, &ctx->cnt->overflow);
+    }
+    CK(cudaGetLastError());
+    // the live count (owned + ghosts) is only known on the device: launch over the whole capacity, kernels exit early
+    ctx->n_host = ctx->cap;
+    ctx->n_exact = false;
+    return 0;
+}
+
+// NOTE: unpack's kernels clamp the appended count on overflow only by flagging; cnt->n may exceed cap by the number
+// of dropped records, every kernel bounds its index by the arrays' capacity through n_host <= cap.
+extern "C" int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int64_t cap, int64_t *n_out) {
+    CKR(dist_ready(ctx, "sc_dist_get_owned"));
+    if (ctx->carry_count) {
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
+        ctx->carry_count = false;
+    }
+    CK(cudaMemsetAsync(&ctx->cnt->n_tmp, 0, sizeof(uint32_t), ctx->stream));
+    const int64_t n = ctx->n_host;
+    if (n > 0) {
+        ProfScope ps(ctx, SLOT_IO);
+        if (ctx->precision == SC_PRECISION_F64)
+            k_dist_collect_owned<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                &ctx->cnt->n, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, ctx->stage2, ctx->pos_srt,
+                (uint32_t *)ctx->stage1, &ctx->cnt->n_tmp);
+        else
+            k_dist_collect_owned<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                &ctx->cnt->n, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur, ctx->stage2, ctx->pos_srt,
+                (uint32_t *)ctx->stage1, &ctx->cnt->n_tmp);
+    }
+    ctx->srt_valid = false;
+    Counters h;
+    CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = h.n_tmp;
+    if ((int64_t)h.n_tmp > cap) return fail(ctx, "sc_dist_get_owned: buffer too small");
+    const size_t m = h.n_tmp;
+    if (m && pos) CK(cudaMemcpyAsync(pos, ctx->stage2, sizeof(double2) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m && vel) CK(cudaMemcpyAsync(vel, ctx->pos_srt, sizeof(double2) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m && uid) CK(cudaMemcpyAsync(uid, ctx->stage1, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// flags raised on the device since the context was created: wire / particle capacity overflow, a particle that
+// moved past a whole halo in one tick.  `send_*_dev` may be NULL.  Synchronises.
+extern "C" int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *send_hi_dev, int *overflow,
+                              int *too_far, int64_t *n_local) {
+    CKR(dist_ready(ctx, "sc_dist_status"));
+    CKR(sync_count(ctx));
+    Counters h;
+    CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    WireHeader w[2] = {};
+    if (send_lo_dev && ctx->dist.has_lo) CK(cudaMemcpyAsync(&w[0], send_lo_dev, sizeof(WireHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    if (send_hi_dev && ctx->dist.has_hi) CK(cudaMemcpyAsync(&w[1], send_hi_dev, sizeof(WireHeader), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (overflow) *overflow = (h.overflow || w[0].overflow || w[1].overflow || h.n > (uint32_t)ctx->cap) ? 1 : 0;
+    if (too_far) *too_far = (w[0].too_far || w[1].too_far) ? 1 : 0;
+    if (n_local) *n_local = h.n;
+    ctx->n_host = ctx->cap;  // back to the conservative launch bound (sync_count narrowed it)
+    ctx->n_exact = false;
+    return 0;
+}

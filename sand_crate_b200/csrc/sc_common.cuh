@@ -62,7 +62,8 @@ struct Counters {
     uint32_t n_pairs;    // sum K_i (filled by the count kernel)
     uint32_t overflow;   // capacity problems seen on the device
     uint32_t pair_cursor;  // next free record of the pair buffer (bump allocator, reset every tick)
-    uint32_t pad_[2];
+    uint32_t n_tmp;        // scratch count (strip decomposition pack / readback)
+    uint32_t pad_[1];
 };
 
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
@@ -76,7 +77,8 @@ __host__ __device__ inline uint64_t tick_key(uint64_t seed, uint64_t tick) {
     return mix64(seed * 0x9E3779B97F4A7C15ULL + tick);
 }
 __device__ inline void pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j, uint32_t &hx, uint32_t &hy) {
-    const uint64_t h = mix64((((uint64_t)uid_i << 32) | (uint64_t)uid_j) ^ tkey);
+    // bit 31 of a uid marks a ghost copy in the strip decomposition (sc_dist.cuh); it is not part of the identity
+    const uint64_t h = mix64((((uint64_t)(uid_i & 0x7FFFFFFFu) << 32) | (uint64_t)(uid_j & 0x7FFFFFFFu)) ^ tkey);
     hx = (uint32_t)(h >> 32);
     hy = (uint32_t)(h & 0xffffffffu);
 }

@@ -227,13 +227,14 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
     const uint32_t beg = cell_start[c], end = cell_start[c + 1];
     const double2 p = pos[i];
     const uint32_t u = uid[i];
+    const uint32_t um = u & 0x7FFFFFFFu;  // ties are broken by identity; bit 31 only marks a ghost copy
     uint32_t rank = 0;
     for (uint32_t m = beg; m < end; ++m) {
         if (m == t) continue;
         const uint32_t j = tmpidx[m];
         const double xj = pos[j].x;
-        const uint32_t uj = uid[j];
-        rank += (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < u)) ? 1u : 0u;
+        const uint32_t uj = uid[j] & 0x7FFFFFFFu;
+        rank += (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < um)) ? 1u : 0u;
     }
     const uint32_t f = beg + rank;
     pos_s[f] = p;

@@ -1,0 +1,172 @@
+"""Strip decomposition of one scene across the GPUs of a box: one process per GPU, `torch.distributed` for the
+plumbing (NCCL over NVLink on GPUs; gloo in the CPU tests), the C ABI's `sc_dist_*` entry points for the device work.
+
+The reference's neighbor search is already a 1-D strip decomposition in y with strip height one diameter
+(collision_detector.py:10-31, 124-128).  The same cell rows are the partition unit here: rank k owns the rows
+`cuts[k] <= floor(y / d) < cuts[k + 1]`, chosen so that every rank starts with the same number of particles.
+
+Per tick:
+
+    pack      device: migrants (row left the strip) + halo copies (within `halo_rows` of a cut) -> two wire buffers
+    exchange  isend / irecv of the fixed-size buffers with rank - 1 and rank + 1 only (open chain: walls at y = 0, 1)
+    unpack    device: migrants become owned particles, halos become ghosts
+    step      the ordinary single-GPU tick on owned + ghosts; the next pack throws the ghosts away
+
+There is no collective on the data path and no host synchronisation: the buffers have a fixed capacity and carry
+their own record count, particle counts stay on the device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+HALO_ROWS = 4  # see DESIGN.md section 6: 1 row of neighbors + 1 row for their pressures/normals + 2 for wall-fix shifts
+INT64_MIN, INT64_MAX = -(2 ** 62), 2 ** 62
+
+
+def rows_of(pos: np.ndarray, diameter: float) -> np.ndarray:
+    """floor(y / d), the reference's strip index (collision_detector.py:126)."""
+    return np.floor(np.asarray(pos)[:, 1] / diameter).astype(np.int64)
+
+
+def partition_rows(rows: np.ndarray, nranks: int, halo_rows: int = HALO_ROWS) -> list[int]:
+    """Row cuts [c_0 = -inf, c_1, ..., c_n = +inf] giving every rank about len(rows) / nranks particles, strips at
+    least 2 * halo_rows high."""
+    if nranks == 1:
+        return [INT64_MIN, INT64_MAX]
+    lo, hi = int(rows.min()), int(rows.max())
+    hist = np.bincount(rows - lo, minlength=hi - lo + 1)
+    cum = np.cumsum(hist)
+    cuts = [INT64_MIN]
+    prev = lo
+    for k in range(1, nranks):
+        target = cum[-1] * k / nranks
+        r = lo + int(np.searchsorted(cum, target, side="left")) + 1  # first row of rank k
+        r = max(r, prev + 2 * halo_rows)
+        cuts.append(r)
+        prev = r
+    cuts.append(INT64_MAX)
+    if cuts[-2] + 2 * halo_rows > hi + 1 and nranks > 1:
+        raise ValueError(f"scene has too few cell rows ({hi - lo + 1}) for {nranks} strips of >= {2 * halo_rows} rows")
+    return cuts
+
+
+class StripDomain:
+    """One rank's share of a strip-decomposed scene.
+
+    `world` is a WorldConfig (closed scenes: no particle sources), `pos` / `vel` the WHOLE initial scene (every rank
+    generates it from the same seed and keeps its rows), uids are the global row indices of `pos`."""
+
+    def __init__(self, world, pos, vel, *, rank: int, world_size: int, precision: str = "mixed",
+                 noise: str = "counter", noise_seed: int = 0, device: int = 0, stream: int | None = None,
+                 halo_rows: int = HALO_ROWS, slack: float = 1.3, wire_capacity: int | None = None,
+                 context_factory=None, tensor_device=None, comm=None):
+        import torch
+
+        if world.particle_sources:
+            raise ValueError("strip decomposition supports closed scenes only (no particle sources)")
+        if noise == "reference":
+            raise ValueError("the reference-RNG noise mode is single-GPU only")
+        self.rank, self.world_size = rank, world_size
+        self.world = world
+        self.halo_rows = halo_rows
+        c = world.coefficients
+        self.diameter = 2 * c["particle_radius"]
+        rows = rows_of(pos, self.diameter)
+        self.cuts = partition_rows(rows, world_size, halo_rows)
+        self.row_lo, self.row_hi = self.cuts[rank], self.cuts[rank + 1]
+        mine = np.nonzero((rows >= self.row_lo) & (rows < self.row_hi))[0]
+        per_row = max(int(np.bincount(rows - rows.min()).max()), 1)
+        self.wire_capacity = int(wire_capacity or max(4 * (halo_rows + 2) * per_row, 1024))
+        capacity = int(len(mine) * slack) + 2 * self.wire_capacity + 1024
+        self.wire_capacity = min(self.wire_capacity, capacity)
+        factory = context_factory or _lib.Context
+        prec = {"f64": _lib.PRECISION_F64, "mixed": _lib.PRECISION_MIXED}[precision]
+        self.ctx = factory(capacity, prec, device, stream)
+        self.ctx.set_params(dt=c["dt"], particle_radius=c["particle_radius"],
+                            wall_collision_decay=c["wall_collision_decay"],
+                            pressure_amplifier=c["pressure_amplifier"], ignored_pressure=c["ignored_pressure"],
+                            collider_noise_level=c["collider_noise_level"], viscosity=c["viscosity"],
+                            surface_smoothing=c["surface_smoothing"], target_pressure=c["target_pressure"],
+                            gravity_x=c["gravity"][0], gravity_y=c["gravity"][1])
+        from .rigid_body import build_rigid_bodies
+        bodies = build_rigid_bodies(world.rigid_bodies)
+        if any(b.kind != "fixed" for b in bodies):
+            raise ValueError("strip decomposition supports fixed walls only")
+        seg = np.vstack([b.segments for b in bodies]) if bodies else np.zeros((0, 2, 2))
+        self.ctx.set_walls(seg, [len(b) for b in bodies], np.array([b.kinematics() for b in bodies]).reshape(-1, 5))
+        self.ctx.set_noise({"counter": _lib.NOISE_COUNTER, "none": _lib.NOISE_NONE}[noise], noise_seed)
+        self.ctx.set_state_uids(pos[mine], vel[mine], mine.astype(np.uint32))
+        self.ctx.dist_configure(rank, world_size, self.row_lo, self.row_hi, halo_rows, self.wire_capacity)
+        self.tick = 0
+
+        nbytes = _lib.wire_bytes(self.wire_capacity) if context_factory is None else 16 + 40 * self.wire_capacity
+        dev = tensor_device if tensor_device is not None else torch.device("cuda", device)
+        mk = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # noqa: E731
+        self.has_lo, self.has_hi = rank > 0, rank < world_size - 1
+        self.send_lo, self.recv_lo = (mk(), mk()) if self.has_lo else (None, None)
+        self.send_hi, self.recv_hi = (mk(), mk()) if self.has_hi else (None, None)
+        self._comm = comm  # torch.distributed module or a test double with batch_isend_irecv / P2POp / isend / irecv
+
+    # ---- one tick ----------------------------------------------------------------------------------------------
+    def exchange(self) -> None:
+        """The only communication of a tick: the two wire buffers, whole, to and from the y-neighbors."""
+        if self.world_size == 1:
+            return
+        import torch.distributed as dist
+        d = self._comm or dist
+        ops = []
+        if self.has_lo:
+            ops.append(d.P2POp(d.isend, self.send_lo, self.rank - 1))
+            ops.append(d.P2POp(d.irecv, self.recv_lo, self.rank - 1))
+        if self.has_hi:
+            ops.append(d.P2POp(d.isend, self.send_hi, self.rank + 1))
+            ops.append(d.P2POp(d.irecv, self.recv_hi, self.rank + 1))
+        for req in d.batch_isend_irecv(ops):
+            req.wait()  # NCCL: the launch stream waits, the host does not
+
+    def physics_tick(self) -> None:
+        self.ctx.set_tick(self.tick)
+        if self.world_size > 1:
+            self.ctx.dist_pack(self.send_lo, self.send_hi)
+            self.exchange()
+            self.ctx.dist_unpack(self.recv_lo, self.recv_hi)
+        self.ctx.step()
+        self.tick += 1
+
+    def step(self, n: int = 1) -> None:
+        for _ in range(n):
+            self.physics_tick()
+
+    # ---- readback ----------------------------------------------------------------------------------------------
+    def owned(self):
+        """(uid, pos, vel) of this rank's particles, sorted by uid."""
+        if self.world_size == 1:
+            pos, vel, _ = self.ctx.get_state(want_pressure=False)
+            return self.ctx.get_uids(), pos, vel
+        pos, vel, uid = self.ctx.dist_get_owned()
+        order = np.argsort(uid, kind="stable")
+        return uid[order], pos[order], vel[order]
+
+    def status(self) -> dict:
+        if self.world_size == 1:
+            return {"overflow": False, "too_far": False, "n_local": self.ctx.particle_count()}
+        return self.ctx.dist_status(self.send_lo, self.send_hi)
+
+    def gather(self):
+        """All ranks' particles on every rank, sorted by uid: the global state in the reference's row order."""
+        uid, pos, vel = self.owned()
+        if self.world_size == 1:
+            return uid, pos, vel
+        import torch.distributed as dist
+        parts = [None] * self.world_size
+        dist.all_gather_object(parts, (uid, pos, vel))
+        uid = np.concatenate([p[0] for p in parts])
+        pos = np.concatenate([p[1] for p in parts])
+        vel = np.concatenate([p[2] for p in parts])
+        order = np.argsort(uid, kind="stable")
+        return uid[order], pos[order], vel[order]
+
+    def close(self) -> None:
+        self.ctx.close()

@@ -85,7 +85,7 @@ class OracleContext:
         seg, bl, bk = self.walls
         mode = self.noise_mode if self.params["collider_noise_level"] != 0 else 0
         out = O.step(self._coeffs(), self.pos, self.vel, seg, bl, bk, noise_mode=mode, noise=noise,
-                     tkey=O.tick_key(self.seed, self.tick), uid=self.uid)
+                     tkey=O.tick_key(self.seed, self.tick), uid=self.uid & np.uint32(0x7FFFFFFF))
         self.pos, self.vel, self.prs = out["pos_out"], out["vel_out"], out["pressure"]
         self.tick += 1
         self._pending = None
@@ -94,3 +94,76 @@ class OracleContext:
         for _ in range(n):
             self.step_begin()
             self.step_finish(None)
+
+    # ---- strip decomposition: the same protocol as sc_dist_* (csrc/sc_dist.cuh), in NumPy -----------------------
+    WIRE_REC = np.dtype([("px", "f8"), ("py", "f8"), ("vx", "f8"), ("vy", "f8"), ("uid", "u4"), ("kind", "u4")])
+    GHOST = np.uint32(0x80000000)
+
+    def set_state_uids(self, pos, vel, uid):
+        self.set_state(pos, vel)
+        self.uid = np.array(uid, dtype=np.uint32)
+        self.next_uid = int(self.uid.max()) + 1 if len(self.uid) else 0
+
+    def dist_configure(self, rank, nranks, row_lo, row_hi, halo_rows, wire_capacity):
+        self.dist = dict(lo=row_lo, hi=row_hi, halo=halo_rows, has_lo=rank > 0, has_hi=rank < nranks - 1,
+                         cap=wire_capacity)
+        self.flags = {"overflow": False, "too_far": False}
+
+    def _write_wire(self, tensor, recs):
+        raw = tensor.numpy()
+        assert len(recs) <= self.dist["cap"], "wire overflow"
+        raw[:16].view(np.uint32)[:] = [len(recs), 0, 0, 0]
+        raw[16:16 + 40 * len(recs)].view(self.WIRE_REC)[:] = recs
+
+    def _read_wire(self, tensor):
+        raw = tensor.numpy()
+        n = int(raw[:16].view(np.uint32)[0])
+        return raw[16:16 + 40 * n].view(self.WIRE_REC).copy()
+
+    def _records(self, mask, kind):
+        r = np.zeros(int(mask.sum()), self.WIRE_REC)
+        r["px"], r["py"] = self.pos[mask, 0], self.pos[mask, 1]
+        r["vx"], r["vy"] = self.vel[mask, 0], self.vel[mask, 1]
+        r["uid"], r["kind"] = self.uid[mask], kind
+        return r
+
+    def dist_pack(self, send_lo, send_hi):
+        D = self.dist
+        keep = (self.uid & self.GHOST) == 0
+        self.pos, self.vel, self.uid = self.pos[keep], self.vel[keep], self.uid[keep]
+        d = 2 * self.params["particle_radius"]
+        rows = np.floor(self.pos[:, 1] / d).astype(np.int64)
+        below = (rows < D["lo"]) & D["has_lo"]
+        above = (rows >= D["hi"]) & D["has_hi"]
+        owned = ~(below | above)
+        if (below & (rows < D["lo"] - D["halo"])).any() or (above & (rows >= D["hi"] + D["halo"])).any():
+            self.flags["too_far"] = True
+        if D["has_lo"]:
+            self._write_wire(send_lo, np.concatenate([self._records(below, 0),
+                                                      self._records(owned & (rows < D["lo"] + D["halo"]), 1)]))
+        if D["has_hi"]:
+            self._write_wire(send_hi, np.concatenate([self._records(above, 0),
+                                                      self._records(owned & (rows >= D["hi"] - D["halo"]), 1)]))
+        self.uid = np.where(owned, self.uid, self.uid | self.GHOST).astype(np.uint32)
+        self.prs = np.zeros(len(self.pos))
+
+    def dist_unpack(self, recv_lo, recv_hi):
+        for has, buf in ((self.dist["has_lo"], recv_lo), (self.dist["has_hi"], recv_hi)):
+            if not has:
+                continue
+            r = self._read_wire(buf)
+            self.pos = np.vstack((self.pos, np.stack((r["px"], r["py"]), 1)))
+            self.vel = np.vstack((self.vel, np.stack((r["vx"], r["vy"]), 1)))
+            self.uid = np.concatenate((self.uid, np.where(r["kind"] == 1, r["uid"] | self.GHOST, r["uid"]))).astype(np.uint32)
+        assert len(self.pos) <= self.capacity, "particle capacity overflow"
+        self.prs = np.zeros(len(self.pos))
+
+    def dist_get_owned(self):
+        own = (self.uid & self.GHOST) == 0
+        return self.pos[own].copy(), self.vel[own].copy(), self.uid[own].copy()
+
+    def dist_status(self, send_lo=None, send_hi=None):
+        return dict(self.flags, n_local=len(self.pos))
+
+    def get_uids(self):
+        return self.uid.copy()

@@ -319,3 +319,19 @@ def test_errors_are_loud():
     ctx.set_state(g["pos_in"][:4], g["vel_in"][:4])
     with pytest.raises(_lib.SandCrateError, match="sc_step_begin"):
         ctx.step()
+
+
+# ---- multi-GPU: strip decomposition over NCCL (needs >= 2 GPUs; skipped on a 1-GPU box) -------------------------
+def test_strips_two_gpus_bit_identical_to_single_gpu():
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tests/mgpu_check.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("bit-identical to single GPU = True") == 3, res.stdout

@@ -1,0 +1,96 @@
+"""Strip decomposition, CPU side: partitioning and the per-tick pack / exchange / unpack protocol over
+`torch.distributed` (gloo, world_size 2 and 3), with the device work done by the oracle-backed test double.  The
+N-rank run must reproduce the single-domain oracle run bit for bit - that is what proves the halo width, the
+migration rule and the ghost retention rule (csrc/sc_dist.cuh) before any GPU is involved."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+from oracle import oracle as O
+from oracle_backend import OracleContext
+from sand_crate_b200.scenes import box_fill, dam_break
+from sand_crate_b200.strips import HALO_ROWS, StripDomain, partition_rows, rows_of
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_partition_rows_balances_and_respects_halo():
+    world, pos, _ = dam_break(40000)
+    d = 2 * world.coefficients["particle_radius"]
+    rows = rows_of(pos, d)
+    for n in (2, 3, 4):
+        cuts = partition_rows(rows, n)
+        assert len(cuts) == n + 1 and cuts[0] < rows.min() and cuts[-1] > rows.max()
+        counts = [int(((rows >= cuts[k]) & (rows < cuts[k + 1])).sum()) for k in range(n)]
+        assert sum(counts) == len(rows)
+        assert max(counts) - min(counts) <= 0.1 * len(rows) / n
+        assert all(cuts[k + 1] - cuts[k] >= 2 * HALO_ROWS for k in range(1, n - 1))
+    with pytest.raises(ValueError):
+        partition_rows(rows[rows < rows.min() + 10], 4)
+
+
+def _coeff_vec(c):
+    return np.array([c["dt"], c["particle_radius"], c["wall_collision_decay"], c["pressure_amplifier"],
+                     c["ignored_pressure"], c["collider_noise_level"], c["viscosity"], c["surface_smoothing"],
+                     c["target_pressure"], c["gravity"][0], c["gravity"][1]], dtype=np.float64)
+
+
+def _worker(rank, world_size, port, scene, n, ticks, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        world, pos, vel = (dam_break if scene == "dam_break" else box_fill)(n)
+        vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0  # fast particles: migration every tick
+        dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision="f64", noise="counter",
+                          noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"))
+        migrated = 0
+        for _ in range(ticks):
+            before = set(dom.ctx.dist_get_owned()[2].tolist())
+            dom.physics_tick()
+            migrated += len(set(dom.ctx.dist_get_owned()[2].tolist()) - before)
+        st = dom.status()
+        uid, p, v = dom.gather()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), uid=uid, pos=p, vel=v)
+        stats = [None] * world_size
+        dist.all_gather_object(stats, (migrated, st["too_far"], st["n_local"]))
+        if rank == 0:
+            np.save(os.path.join(out_dir, "stats.npy"), np.array(stats, dtype=np.int64))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size,scene", [(2, "dam_break"), (3, "box_fill")])
+def test_strip_protocol_matches_single_domain(tmp_path, world_size, scene):
+    n, ticks = 6000, 6
+    mp.spawn(_worker, args=(world_size, _free_port(), scene, n, ticks, str(tmp_path)), nprocs=world_size, join=True)
+    got = np.load(tmp_path / "out.npz")
+    stats = np.load(tmp_path / "stats.npy")
+    # reference: the same ticks on the whole scene in one domain
+    world, pos, vel = (dam_break if scene == "dam_break" else box_fill)(n)
+    vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = _coeff_vec(world.coefficients)
+    uid = np.arange(n, dtype=np.uint32)
+    for tick in range(ticks):
+        pos, vel, mask = O.remove_particles(pos, vel, world.coefficients["particle_radius"])
+        uid = uid[~mask]
+        out = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(11, tick), uid=uid,
+                     want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+    assert np.array_equal(got["uid"], uid)
+    assert np.array_equal(got["pos"], pos) and np.array_equal(got["vel"], vel)
+    assert stats[:, 0].sum() > 0, "the test scene must exercise migration"
+    assert not stats[:, 1].any(), "no particle may cross a whole halo in one tick"
