@@ -147,6 +147,15 @@ int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t
                       int64_t wire_capacity);
 int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev);
 int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev);
+/* Direct NVLink transport instead of send/recv.  sc_dist_push copies header + used records of both packed buffers
+ * into the neighbors' receive buffers through peer-mapped device pointers (e.g. torch symmetric memory) and then
+ * stores `value` (release, system scope) to each neighbor's flag word; sc_dist_unpack_flagged is sc_dist_unpack whose
+ * kernel first waits (on the device) until this rank's flag words have reached `value`.  Use the tick number as
+ * `value`: monotonic, never reset.  NULL where there is no neighbor. */
+int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev,
+                 const void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value);
+int sc_dist_unpack_flagged(sc_ctx *ctx, const void *recv_lo_dev, const void *flag_lo_dev, const void *recv_hi_dev,
+                           const void *flag_hi_dev, uint32_t value);
 /* owned particles of this rank, in arbitrary order; uid[i] identifies row i.  Synchronises. */
 int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int64_t cap, int64_t *n);
 /* device-side flags since creation: capacity overflow, a particle that crossed a whole halo in one tick; the

@@ -64,7 +64,8 @@ struct sc_ctx {
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
     bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
     DistCfg dist{};
-    WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers
+    WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers (+ push completion counters)
+    unsigned push_toggle = 0;
     int64_t launches = 0;
     bool profiling = false;
     std::vector<ProfEvent> pending;
@@ -168,6 +169,23 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
 static void refresh_wall_boxes(sc_ctx *ctx);
 static int sync_count(sc_ctx *ctx);
 
+// Cell grid of the world box; in strip mode only the rows this rank can ever hold (its strip, the halo, and the
+// one-row shift the wall fix can add), so clearing and scanning the grid scales with the strip, not the scene.
+static int world_grid(sc_ctx *ctx) {
+    // live particles satisfy -r <= coord <= 1 + r (crate.py:152) and apply_hard_wall_fix moves by < r
+    const double d = ctx->dp.d, r = ctx->dp.r;
+    const int lo = (int)std::floor((-2 * r) / d) - 1, hi = (int)std::floor((1 + 2 * r) / d) + 1;
+    int rlo = lo, rhi = hi;
+    if (ctx->dist_on) {
+        const long long margin = ctx->dist.halo + 2;
+        if (ctx->dist.has_lo && ctx->dist.row_lo - margin > rlo) rlo = (int)(ctx->dist.row_lo - margin);
+        if (ctx->dist.has_hi && ctx->dist.row_hi + margin < rhi) rhi = (int)(ctx->dist.row_hi + margin);
+    }
+    CKR(setup_grid(ctx, d, rlo, rhi, lo, hi));
+    ctx->srt_valid = false;
+    return 0;
+}
+
 static int refresh_dev_params(sc_ctx *ctx) {
     const sc_params &h = ctx->hp;
     DevParams &p = ctx->dp;
@@ -259,12 +277,9 @@ extern "C" int sc_set_params(sc_ctx *ctx, const sc_params *p) {
     refresh_dev_params(ctx);
     if (regrid) {
         // live particles satisfy -r <= coord <= 1 + r (crate.py:152) and apply_hard_wall_fix moves by < r
-        const double d = ctx->dp.d, r = ctx->dp.r;
-        const int lo = (int)std::floor((-2 * r) / d) - 1, hi = (int)std::floor((1 + 2 * r) / d) + 1;
-        CKR(setup_grid(ctx, d, lo, hi, lo, hi));
-        ctx->srt_valid = false;
+        CKR(world_grid(ctx));
         if (ctx->walls_set) {
-            sc_pad_segments(&ctx->walls.seg[0][0], ctx->walls.S, r, &ctx->walls.pad[0][0]);
+            sc_pad_segments(&ctx->walls.seg[0][0], ctx->walls.S, ctx->dp.r, &ctx->walls.pad[0][0]);
             refresh_wall_boxes(ctx);
         }
     }
@@ -961,8 +976,15 @@ extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_
     ctx->dist.row_lo = row_lo; ctx->dist.row_hi = row_hi; ctx->dist.halo = halo_rows;
     ctx->dist.has_lo = rank > 0; ctx->dist.has_hi = rank < nranks - 1;
     ctx->dist.cap = (uint32_t)wire_capacity;
-    if (!ctx->wire_dummy) CKR(dev_alloc(ctx, &ctx->wire_dummy, 2));
+    if (!ctx->wire_dummy) {
+        CKR(dev_alloc(ctx, &ctx->wire_dummy, 4));
+        CK(cudaMemsetAsync(ctx->wire_dummy, 0, sizeof(WireHeader) * 4, ctx->stream));
+    }
     ctx->dist_on = true;
+    if (ctx->params_set) {
+        CKR(sync_count(ctx));  // the live count may sit in the old cell array's tail
+        CKR(world_grid(ctx));
+    }
     return 0;
 }
 
@@ -1008,25 +1030,59 @@ extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     return 0;
 }
 
-extern "C" int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev) {
-    CKR(dist_ready(ctx, "sc_dist_unpack"));
-    const void *bufs[2] = {ctx->dist.has_lo ? recv_lo_dev : nullptr, ctx->dist.has_hi ? recv_hi_dev : nullptr};
-    for (int q = 0; q < 2; ++q) {
-        if (!bufs[q]) continue;
+static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, const void *recv_hi,
+                          const void *flag_hi, uint32_t value) {
+    UnpackSide lo{ctx->dist.has_lo ? (const WireHeader *)recv_lo : nullptr, (const uint32_t *)flag_lo};
+    UnpackSide hi{ctx->dist.has_hi ? (const WireHeader *)recv_hi : nullptr, (const uint32_t *)flag_hi};
+    if (lo.hdr || hi.hdr) {
         ProfScope ps(ctx, SLOT_IO);
+        const dim3 grid(blocks_for(ctx->dist.cap), 2);
         if (ctx->precision == SC_PRECISION_F64)
-            k_dist_unpack<double><<<blocks_for(ctx->dist.cap), SC_BLOCK, 0, ctx->stream>>>(
-                (const WireHeader *)bufs[q], ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur,
-                &ctx->cnt->n, (uint32_t)ctx->cap, &ctx->cnt->overflow);
+            k_dist_unpack<double><<<grid, SC_BLOCK, 0, ctx->stream>>>(
+                lo, hi, value, ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
+                (uint32_t)ctx->cap, &ctx->cnt->overflow);
         else
-            k_dist_unpack<float><<<blocks_for(ctx->dist.cap), SC_BLOCK, 0, ctx->stream>>>(
-                (const WireHeader *)bufs[q], ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur,
-                &ctx->cnt->n, (uint32_t)ctx->cap, &ctx->cnt->overflow);
+            k_dist_unpack<float><<<grid, SC_BLOCK, 0, ctx->stream>>>(
+                lo, hi, value, ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
+                (uint32_t)ctx->cap, &ctx->cnt->overflow);
     }
     CK(cudaGetLastError());
     // the live count (owned + ghosts) is only known on the device: launch over the whole capacity, kernels exit early
     ctx->n_host = ctx->cap;
     ctx->n_exact = false;
+    return 0;
+}
+
+extern "C" int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev) {
+    CKR(dist_ready(ctx, "sc_dist_unpack"));
+    return enqueue_unpack(ctx, recv_lo_dev, nullptr, recv_hi_dev, nullptr, 0);
+}
+
+extern "C" int sc_dist_unpack_flagged(sc_ctx *ctx, const void *recv_lo_dev, const void *flag_lo_dev,
+                                      const void *recv_hi_dev, const void *flag_hi_dev, uint32_t value) {
+    CKR(dist_ready(ctx, "sc_dist_unpack_flagged"));
+    return enqueue_unpack(ctx, recv_lo_dev, flag_lo_dev, recv_hi_dev, flag_hi_dev, value);
+}
+
+extern "C" int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev,
+                            const void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value) {
+    CKR(dist_ready(ctx, "sc_dist_push"));
+    uint32_t *done = reinterpret_cast<uint32_t *>(ctx->wire_dummy + 2);  // "blocks done" counters, one per direction
+    PushSide lo{nullptr, nullptr, nullptr, done}, hi{nullptr, nullptr, nullptr, done + 1};
+    if (ctx->dist.has_lo) {
+        if (!send_lo_dev || !peer_recv_lo_dev || !peer_flag_lo_dev) return fail(ctx, "sc_dist_push: NULL lower buffer");
+        lo.src = (const WireHeader *)send_lo_dev; lo.peer_dst = peer_recv_lo_dev; lo.peer_flag = (uint32_t *)peer_flag_lo_dev;
+    }
+    if (ctx->dist.has_hi) {
+        if (!send_hi_dev || !peer_recv_hi_dev || !peer_flag_hi_dev) return fail(ctx, "sc_dist_push: NULL upper buffer");
+        hi.src = (const WireHeader *)send_hi_dev; hi.peer_dst = peer_recv_hi_dev; hi.peer_flag = (uint32_t *)peer_flag_hi_dev;
+    }
+    if (!lo.src && !hi.src) return 0;
+    ProfScope ps(ctx, SLOT_IO);
+    const size_t bytes = sizeof(WireHeader) + (size_t)ctx->dist.cap * sizeof(WireRec);
+    const unsigned nb = (unsigned)std::min<size_t>((bytes / 16 + SC_BLOCK - 1) / SC_BLOCK, 64);
+    k_wire_push<<<dim3(nb, 2), SC_BLOCK, 0, ctx->stream>>>(lo, hi, ctx->dist.cap, value);
+    CK(cudaGetLastError());
     return 0;
 }
 

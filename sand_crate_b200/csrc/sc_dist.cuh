@@ -83,15 +83,35 @@ k_dist_pack(Counters *__restrict__ cnt, const uint32_t *__restrict__ n_in_ptr, G
     uid_out[k] = tag;
 }
 
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == NULL: the data is already there
+
+// both neighbors' buffers in one launch (blockIdx.y = side).  With the direct NVLink transport every block first
+// waits for its side's flag to reach `value` (raised by the neighbor's k_wire_push, which runs on another GPU).
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_dist_unpack(const WireHeader *__restrict__ hdr, uint32_t wire_cap, double2 *__restrict__ pos,
+k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, double2 *__restrict__ pos,
               typename Vec2<Real>::type *__restrict__ vel, uint32_t *__restrict__ uid, uint32_t *__restrict__ n,
               uint32_t cap, uint32_t *__restrict__ overflow) {
+    const UnpackSide side = blockIdx.y ? hi : lo;
+    if (!side.hdr) return;
+    if (side.flag) {
+        if (threadIdx.x == 0)
+            while ((int)(ld_acquire_sys(side.flag) - value) < 0) __nanosleep(64);
+        __syncthreads();
+    }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = hdr->count < wire_cap ? hdr->count : wire_cap;
+    const uint32_t count = side.hdr->count < wire_cap ? side.hdr->count : wire_cap;
     if (i >= count) return;
-    const WireRec r = reinterpret_cast<const WireRec *>(hdr + 1)[i];
+    const WireRec r = reinterpret_cast<const WireRec *>(side.hdr + 1)[i];
     const uint32_t k = atomicAdd(n, 1u);
     if (k >= cap) { *overflow = 1u; return; }
     pos[k] = make_double2(r.px, r.py);
@@ -117,6 +137,35 @@ k_dist_collect_owned(const uint32_t *__restrict__ n_ptr, const double2 *__restri
     const typename Vec2<Real>::type v = vel[i];
     vel_out[k] = make_double2((double)v.x, (double)v.y);
     uid_out[k] = u;
+}
+
+// Direct NVLink transport: copies the used part of a packed wire buffer (header + count records) into the neighbor's
+// receive buffer through a peer-mapped pointer (torch symmetric memory), then raises the neighbor's flag: every block
+// fences its stores to system scope and the last block to finish publishes `value` (the tick number, monotonic,
+// so flags are never reset).  The receiver's unpack kernel spins on the flag - the two kernels run on different
+// GPUs, so neither waits for a launch on its own device.
+struct PushSide { const WireHeader *src; void *peer_dst; uint32_t *peer_flag; uint32_t *done; };
+
+__global__ void __launch_bounds__(SC_BLOCK)
+k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
+    const PushSide side = blockIdx.y ? hi : lo;
+    if (!side.src) return;
+    const uint32_t count = side.src->count < cap ? side.src->count : cap;
+    const size_t bytes = sizeof(WireHeader) + (size_t)count * sizeof(WireRec);
+    const size_t chunks = (bytes + 15) / 16;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(side.src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(side.peer_dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x)
+        d4[i] = s4[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(side.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *side.done = 0u;
+            st_release_sys(side.peer_flag, value);
+        }
+    }
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b, uint32_t *n_out) {

@@ -61,7 +61,7 @@ class StripDomain:
     def __init__(self, world, pos, vel, *, rank: int, world_size: int, precision: str = "mixed",
                  noise: str = "counter", noise_seed: int = 0, device: int = 0, stream: int | None = None,
                  halo_rows: int = HALO_ROWS, slack: float = 1.3, wire_capacity: int | None = None,
-                 context_factory=None, tensor_device=None, comm=None):
+                 context_factory=None, tensor_device=None, comm=None, transport: str = "nccl"):
         import torch
 
         if world.particle_sources:
@@ -108,6 +108,62 @@ class StripDomain:
         self.send_lo, self.recv_lo = (mk(), mk()) if self.has_lo else (None, None)
         self.send_hi, self.recv_hi = (mk(), mk()) if self.has_hi else (None, None)
         self._comm = comm  # torch.distributed module or a test double with batch_isend_irecv / P2POp / isend / irecv
+        if transport not in ("nccl", "p2p", "auto"):
+            raise ValueError("transport must be 'nccl', 'p2p' or 'auto'")
+        self.transport = transport
+        self._symm = None
+        if transport in ("p2p", "auto") and world_size > 1 and context_factory is None:
+            try:
+                self._setup_p2p(nbytes, dev)
+                ok = 1
+            except Exception:  # no peer access / no symmetric memory on this box
+                if transport == "p2p":
+                    raise
+                ok = 0
+            if transport == "auto":  # every rank must take the same path
+                import torch.distributed as dist
+                flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    self._symm = None
+                self.transport = "p2p" if self._symm is not None else "nccl"
+        elif transport == "auto":
+            self.transport = "nccl"
+
+    # ---- direct NVLink transport (torch symmetric memory): peer stores + stream signals, no NCCL call per tick ----
+    def _setup_p2p(self, nbytes: int, dev) -> None:
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        slot = (nbytes + 255) // 256 * 256
+        # layout: 256 bytes of flags, then [parity 0: from-lo | from-hi][parity 1: from-lo | from-hi]; double buffered
+        # so that a neighbor one tick ahead never overwrites records this rank has not unpacked yet.
+        # flag word (parity, side) at byte 64 * (2 * parity + side): last tick whose records have fully arrived.
+        self._symm_buf = symm_mem.empty(256 + 4 * slot, dtype=torch.uint8, device=dev)
+        self._symm_buf.zero_()
+        self._symm = symm_mem.rendezvous(self._symm_buf, dist.group.WORLD.group_name)
+        self._slot = slot
+        self._peer = [int(p) for p in self._symm.buffer_ptrs]
+        torch.cuda.synchronize()
+        self._symm.barrier(channel=0)
+
+    def _exchange_p2p(self) -> None:
+        par = self.tick & 1
+        data = 256 + 2 * par * self._slot
+        value = self.tick + 1
+        lo = hi = None
+        # my lower neighbor receives "from hi" (side 1), my upper neighbor receives "from lo" (side 0)
+        if self.has_lo:
+            peer = self._peer[self.rank - 1]
+            lo = (self.send_lo, peer + data + self._slot, peer + 64 * (2 * par + 1))
+        if self.has_hi:
+            peer = self._peer[self.rank + 1]
+            hi = (self.send_hi, peer + data, peer + 64 * (2 * par))
+        self.ctx.dist_push(lo, hi, value)
+        mine = self._peer[self.rank]
+        self.ctx.dist_unpack_flagged((mine + data, mine + 64 * (2 * par)) if self.has_lo else None,
+                                     (mine + data + self._slot, mine + 64 * (2 * par + 1)) if self.has_hi else None,
+                                     value)
 
     # ---- one tick ----------------------------------------------------------------------------------------------
     def exchange(self) -> None:
@@ -130,8 +186,11 @@ class StripDomain:
         self.ctx.set_tick(self.tick)
         if self.world_size > 1:
             self.ctx.dist_pack(self.send_lo, self.send_hi)
-            self.exchange()
-            self.ctx.dist_unpack(self.recv_lo, self.recv_hi)
+            if self._symm is not None:
+                self._exchange_p2p()
+            else:
+                self.exchange()
+                self.ctx.dist_unpack(self.recv_lo, self.recv_hi)
         self.ctx.step()
         self.tick += 1
 

@@ -30,12 +30,13 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ok = True
+    transport = os.environ.get("SC_TRANSPORT", "nccl")
     for maker, n, ticks, precision in ((dam_break, 200_000, 12, "f64"), (box_fill, 300_000, 8, "f64"),
                                        (dam_break, 200_000, 12, "mixed")):
         world_cfg, pos, vel = maker(n)
         vel = vel + np.random.RandomState(3).randn(*vel.shape) * (2.0 * world_cfg.coefficients["particle_radius"] / world_cfg.coefficients["dt"]) * 0.3
         dom = StripDomain(world_cfg, pos, vel, rank=rank, world_size=world, precision=precision, noise="counter",
-                          noise_seed=5, device=local, stream=stream.cuda_stream)
+                          noise_seed=5, device=local, stream=stream.cuda_stream, transport=transport)
         own0 = set(dom.owned()[0].tolist())
         dom.step(ticks)
         st = dom.status()
@@ -50,7 +51,7 @@ def main():
             suid, sp, sv = single.gather()
             same = np.array_equal(uid, suid) and np.array_equal(gp, sp) and np.array_equal(gv, sv)
             flags = any(s["overflow"] or s["too_far"] for _, s in moved_all)
-            print(f"[mgpu] {maker.__name__} n={n} ticks={ticks} {precision} ranks={world}: "
+            print(f"[mgpu] transport={transport} {maker.__name__} n={n} ticks={ticks} {precision} ranks={world}: "
                   f"bit-identical to single GPU = {same}; migrated = {[m for m, _ in moved_all]}; "
                   f"local = {[s['n_local'] for _, s in moved_all]}; flags = {flags}", flush=True)
             ok = ok and same and not flags and sum(m for m, _ in moved_all) > 0
