@@ -91,6 +91,18 @@ static int fail(sc_ctx *c, const std::string &m) {
         if (r_) return r_;   \
     } while (0)
 
+// launch with programmatic stream serialization (see pdl_enter in sc_common.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + SC_BLOCK - 1) / SC_BLOCK); }
 
 struct ProfScope {
@@ -482,7 +494,7 @@ static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot, bool p
     }
     if (!pre_cleared) CK(cudaMemsetAsync(ctx->bsum, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
     ProfScope ps(ctx, slot);
-    k_scan_lookback<<<nb, SC_SCAN_THREADS, 0, ctx->stream>>>(a, n, ctx->bsum + 1, (uint32_t *)ctx->bsum);
+    CK(launch_pdl(k_scan_lookback, dim3(nb), dim3(SC_SCAN_THREADS), ctx->stream, a, n, ctx->bsum + 1, (uint32_t *)ctx->bsum));
     return 0;
 }
 
@@ -523,35 +535,35 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         const uint32_t words = (uint32_t)(n / 32 + 1);
         const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
         const uint32_t scan_words = (g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;  // ticket + descriptors
-        k_begin_tick<<<nb, SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start, g.ncells, ctx->carry_count ? 1 : 0,
-                                                       ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum,
-                                                       scan_words);
+        CK(launch_pdl(k_begin_tick, dim3(nb), dim3(SC_BLOCK), ctx->stream, ctx->cnt, ctx->cell_start, g.ncells,
+                      ctx->carry_count ? 1 : 0, ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum, scan_words));
         ctx->carry_count = false;
     }
     if (n > 0) {
         ProfScope ps(ctx, SLOT_PREPASS);
-        k_prepass<kStep><<<blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP), SC_BLOCK, 0, ctx->stream>>>(
-            ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot, ctx->cell_start,
-            ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre);
+        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
+                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre));
     }
     CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
         {
             ProfScope ps(ctx, SLOT_PLACE);
-            k_place<<<blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP), SC_BLOCK, 0, ctx->stream>>>(ctx->cnt, ctx->cell_key, ctx->slot, ctx->cell_start,
-                                                                 ctx->tmpidx);
+            CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
+                          (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
+                          (const uint32_t *)ctx->cell_start, ctx->tmpidx));
         }
         ProfScope ps(ctx, SLOT_RANK_GATHER);
         if (ctx->precision == SC_PRECISION_F64)
-            k_rank_gather<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_pdl(k_rank_gather<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
                 ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt));
         else
-            k_rank_gather<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_pdl(k_rank_gather<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
                 ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt);
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt));
     }
     CK(cudaGetLastError());
     ctx->srt_valid = true;
@@ -596,29 +608,29 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
         if (ctx->precision == SC_PRECISION_F64) {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
-                k_density<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                CK(launch_pdl(k_density<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                     ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
                     ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (double2 *)ctx->pair_n, ctx->pair_off,
-                    ctx->pair_cnt, (PS<double> *)ctx->ps);
+                    ctx->pair_cnt, (PS<double> *)ctx->ps));
             }
             ProfScope ps(ctx, SLOT_FORCE);
-            k_force<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_pdl(k_force<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 n_ptr, dp, ctx->walls, ctx->pos_srt, (const double2 *)ctx->vel_srt, ctx->pair_j,
                 (const double2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<double> *)ctx->ps,
-                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur);
+                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur));
         } else {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
-                k_density<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+                CK(launch_pdl(k_density<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                     ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
                     ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (float2 *)ctx->pair_n, ctx->pair_off,
-                    ctx->pair_cnt, (PS<float> *)ctx->ps);
+                    ctx->pair_cnt, (PS<float> *)ctx->ps));
             }
             ProfScope ps(ctx, SLOT_FORCE);
-            k_force<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_pdl(k_force<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 n_ptr, dp, ctx->walls, ctx->pos_srt, (const float2 *)ctx->vel_srt, ctx->pair_j,
                 (const float2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps,
-                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur);
+                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur));
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count

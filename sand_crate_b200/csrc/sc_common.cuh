@@ -15,6 +15,15 @@
 
 namespace sc {
 
+// Programmatic dependent launch (sm_90+): the step's kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks may become resident while the
+// current kernel drains.  pdl_enter() = let the dependent kernel start launching, then wait until everything the
+// preceding kernel wrote is visible.  A no-op for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // uniform cell grid with cell edge = one particle diameter; row = floor(y / d) is the reference's strip index
 // (collision_detector.py:126), col = floor(x / d) is ours (monotone in x, so a cell-major order
 // (row, col, x, uid) is the same permutation as np.lexsort((x, row)), collision_detector.py:127).

@@ -197,6 +197,7 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
           const uint32_t *__restrict__ noise_off, const uint32_t *__restrict__ rank_of_uid,
           uint32_t *__restrict__ pair_j, typename Vec2<Real>::type *__restrict__ pair_n,
           uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, PS<Real> *__restrict__ ps_out) {
+    pdl_enter();
     __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
     __shared__ uint32_t s_base;
     const uint32_t n = cell_start[g.ncells];
@@ -269,6 +270,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
         const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
         double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out) {
+    pdl_enter();
     typedef typename Vec2<Real>::type R2;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;

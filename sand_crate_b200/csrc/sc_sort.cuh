@@ -21,6 +21,7 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
           double2 *__restrict__ pos, uint32_t *__restrict__ cell_key, uint32_t *__restrict__ slot,
           uint32_t *__restrict__ cell_count, uint32_t *__restrict__ wall_bits, uint32_t *__restrict__ wall_slot,
           double2 *__restrict__ wall_pre) {
+    pdl_enter();
     const uint32_t n = cnt->n;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
     double2 p[SC_PREPASS_ILP];
@@ -126,6 +127,7 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 __global__ void __launch_bounds__(SC_SCAN_THREADS)
 k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__restrict__ desc,
                 uint32_t *__restrict__ ticket) {
+    pdl_enter();
     __shared__ uint32_t s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -190,6 +192,7 @@ k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__rest
 __global__ void __launch_bounds__(SC_BLOCK)
 k_place(const Counters *__restrict__ cnt, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ slot,
         const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ tmpidx) {
+    pdl_enter();
     const uint32_t n = cnt->n;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
     uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP];
@@ -219,6 +222,7 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
               typename Vec2<Real>::type *__restrict__ vel_s, uint32_t *__restrict__ uid_s,
               uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
               uint32_t *__restrict__ wall_slot_s) {
+    pdl_enter();
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(SC_BLOCK)
 k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, int carry_count,
              uint32_t *__restrict__ bits_a, uint32_t *__restrict__ bits_b, uint32_t nbits_words,
              unsigned long long *__restrict__ scan_desc, uint32_t scan_words) {
+    pdl_enter();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
