@@ -34,7 +34,7 @@ typedef struct {
 } oc_params;
 
 /* ------------------------------------------------------------------------------------------------------ */
-/* counter-based pair noise: the PRODUCT's definition (sand_crate_b200/csrc/noise.cuh), restated here so an   */
+/* counter-based pair noise: the PRODUCT's definition (sand_crate_b200/csrc/sc_common.cuh), restated here so an */
 /* oracle run can consume exactly the same uniforms as the GPU's production mode.                            */
 static inline uint64_t oc_mix64(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
@@ -43,10 +43,18 @@ static inline uint64_t oc_mix64(uint64_t z) {
     return z;
 }
 uint64_t oc_tick_key(uint64_t seed, uint64_t tick) { return oc_mix64(seed * 0x9E3779B97F4A7C15ULL + tick); }
+static inline uint32_t oc_lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
 void oc_pair_noise(uint64_t tick_key, uint32_t uid_i, uint32_t uid_j, double *ux, double *uy) {
-    uint64_t h = oc_mix64((((uint64_t)uid_i << 32) | (uint64_t)uid_j) ^ tick_key);
-    *ux = (double)(uint32_t)(h >> 32) * (1.0 / 4294967296.0);
-    *uy = (double)(uint32_t)(h & 0xffffffffu) * (1.0 / 4294967296.0);
+    const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
+    const uint32_t hx = oc_lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (uint32_t)tick_key);
+    const uint32_t hy = oc_lowbias32(hx ^ (uint32_t)(tick_key >> 32));
+    *ux = (double)hx * (1.0 / 4294967296.0);
+    *uy = (double)hy * (1.0 / 4294967296.0);
 }
 
 /* ------------------------------------------------------------------------------------------------------ */

@@ -596,6 +596,23 @@ static int enqueue_count(sc_ctx *ctx, const uint32_t *uid, bool want_lists) {
     return 0;
 }
 
+template <typename Real>
+static int launch_density(sc_ctx *ctx, const Grid &g, const DevParams &dp, const uint32_t *noise_off, int64_t n) {
+    typedef typename Vec2<Real>::type R2;
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt, g, dp, ctx->cell_start,
+                          ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt, ctx->noise_dev, noise_off,
+                          ctx->rank_of_uid, ctx->pair_j, (R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
+                          (PS<Real> *)ctx->ps);
+    };
+    cudaError_t e;
+    if (dp.noise_mode == SC_NOISE_HOST) e = go(k_density<Real, SC_NOISE_HOST>);
+    else if (dp.noise_mode == SC_NOISE_COUNTER) e = go(k_density<Real, SC_NOISE_COUNTER>);
+    else e = go(k_density<Real, SC_NOISE_NONE>);
+    CK(e);
+    return 0;
+}
+
 static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
     const int64_t n = ctx->n_host;
     const Grid &g = ctx->grid;
@@ -608,10 +625,7 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
         if (ctx->precision == SC_PRECISION_F64) {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
-                CK(launch_pdl(k_density<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
-                    ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (double2 *)ctx->pair_n, ctx->pair_off,
-                    ctx->pair_cnt, (PS<double> *)ctx->ps));
+                CKR(launch_density<double>(ctx, g, dp, noise_off, n));
             }
             ProfScope ps(ctx, SLOT_FORCE);
             CK(launch_pdl(k_force<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
@@ -621,10 +635,7 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
         } else {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
-                CK(launch_pdl(k_density<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                    ctx->cnt, g, dp, ctx->cell_start, ctx->pos_srt, ctx->rel_srt, ctx->cell_key_srt, ctx->uid_srt,
-                    ctx->noise_dev, noise_off, ctx->rank_of_uid, ctx->pair_j, (float2 *)ctx->pair_n, ctx->pair_off,
-                    ctx->pair_cnt, (PS<float> *)ctx->ps));
+                CKR(launch_density<float>(ctx, g, dp, noise_off, n));
             }
             ProfScope ps(ctx, SLOT_FORCE);
             CK(launch_pdl(k_force<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,

@@ -76,6 +76,11 @@ struct Counters {
 };
 
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
+// Host side: tick_key = splitmix64 finalizer of (seed, tick).  Device side, per DIRECTED pair (i <- j), 32-bit
+// arithmetic only: the two uids are spread with distinct odd multipliers, keyed with the low word of tick_key and
+// mixed with the lowbias32 finalizer (2 multiplies, 3 xor-shifts) for the x uniform; the y uniform is a second
+// lowbias32 round keyed with the high word.  Bit 31 of a uid marks a ghost copy in the strip decomposition
+// (sc_dist.cuh) and is not part of the identity.
 __host__ __device__ inline uint64_t mix64(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
     z ^= z >> 27; z *= 0x94D049BB133111EBULL;
@@ -85,11 +90,16 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {
 __host__ __device__ inline uint64_t tick_key(uint64_t seed, uint64_t tick) {
     return mix64(seed * 0x9E3779B97F4A7C15ULL + tick);
 }
-__device__ inline void pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j, uint32_t &hx, uint32_t &hy) {
-    // bit 31 of a uid marks a ghost copy in the strip decomposition (sc_dist.cuh); it is not part of the identity
-    const uint64_t h = mix64((((uint64_t)(uid_i & 0x7FFFFFFFu) << 32) | (uint64_t)(uid_j & 0x7FFFFFFFu)) ^ tkey);
-    hx = (uint32_t)(h >> 32);
-    hy = (uint32_t)(h & 0xffffffffu);
+__host__ __device__ inline uint32_t lowbias32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ inline void pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j, uint32_t &hx, uint32_t &hy) {
+    const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
+    hx = lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (uint32_t)tkey);
+    hy = lowbias32(hx ^ (uint32_t)(tkey >> 32));
 }
 
 // ---- geometry_utils.py:7-39 for one (point, segment) -----------------------------------------------------

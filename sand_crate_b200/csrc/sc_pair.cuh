@@ -25,7 +25,7 @@ template <> struct __align__(32) PS<double> { double p, sx, sy, pad_; };
 
 // Per-thread neighbor list kept in shared memory, one column per thread (conflict-free: slot k of thread t is
 // word k * SC_BLOCK + t).  An entry is the neighbor's sorted index in the low 28 bits and the relative cell
-// (dr + 1) * 3 + (dc + 1) in the high 4.
+// (dr + 1) * 4 + (dc + 1) in the high 4.
 #define SC_IDX_MASK 0x0FFFFFFFu
 struct NbrList {
     uint32_t *col;
@@ -82,7 +82,7 @@ __device__ __forceinline__ int collect_neighbors(uint32_t s, uint32_t c, const G
             /* qd > hi: surely farther than d (NaN lands here too: the reference rejects NaN); qd < lo: inside */ \
             if (qd <= hi && (qd < lo || accept_exact(pos[s], pos[j], g.d, (DR), (ASC)))) {                       \
                 const int dc = (int)(j >= (B1)) + (int)(j >= (B2)) - 1;                                          \
-                lst.set(count, j | ((uint32_t)(((DR) + 1) * 3 + (dc + 1)) << 28));                               \
+                lst.set(count, j | ((uint32_t)(((DR) + 1) * 4 + (dc + 1)) << 28));                               \
                 ++count;                                                                                         \
             }                                                                                                    \
         }                                                                                                        \
@@ -99,13 +99,14 @@ __device__ __forceinline__ int collect_neighbors(uint32_t s, uint32_t c, const G
 // w = 1 - clip(dist / d, 0, 1) (crate.py:270).
 template <typename Real> struct PairGeom { Real nx, ny, w; };
 
+template <int kNoise>
 __device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, double2 pi, double2 pj, uint32_t uid_i,
                                                           uint32_t uid_j, const double *__restrict__ host_noise,
                                                           uint32_t noise_index) {
     double qx = pj.x, qy = pj.y;
-    if (P.noise_mode != SC_NOISE_NONE) {
+    if constexpr (kNoise != SC_NOISE_NONE) {
         double ux, uy;
-        if (P.noise_mode == SC_NOISE_HOST) {
+        if constexpr (kNoise == SC_NOISE_HOST) {
             ux = host_noise[2 * (size_t)noise_index];
             uy = host_noise[2 * (size_t)noise_index + 1];
         } else {
@@ -131,19 +132,21 @@ __device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, do
 
 // fp32 flavour: (rx, ry) = p_i - p_j formed from the cell-relative coordinates (absolute fp32 coordinates would lose
 // 1e-4-level precision in the weights at d ~ 1e-4)
+template <int kNoise>
 __device__ __forceinline__ PairGeom<float> pair_geom_f32(const DevParams &P, float rx, float ry, uint32_t uid_i,
                                                          uint32_t uid_j, const double *__restrict__ host_noise,
                                                          uint32_t noise_index) {
-    if (P.noise_mode != SC_NOISE_NONE) {
+    if constexpr (kNoise != SC_NOISE_NONE) {
         float ux, uy;
-        if (P.noise_mode == SC_NOISE_HOST) {
+        if constexpr (kNoise == SC_NOISE_HOST) {
             ux = (float)host_noise[2 * (size_t)noise_index];
             uy = (float)host_noise[2 * (size_t)noise_index + 1];
         } else {
             uint32_t hx, hy;
             pair_noise_bits(P.tick_key, uid_i, uid_j, hx, hy);
-            ux = (float)hx * (1.0f / 4294967296.0f);
-            uy = (float)hy * (1.0f / 4294967296.0f);
+            // top 23 bits into the mantissa of [1, 2): no integer-to-float conversion on the hot path
+            ux = __uint_as_float(0x3F800000u | (hx >> 9)) - 1.0f;
+            uy = __uint_as_float(0x3F800000u | (hy >> 9)) - 1.0f;
         }
         const float amp = (float)(P.d * P.level);
         rx = fmaf(0.5f - ux, amp, rx);
@@ -189,7 +192,7 @@ __device__ inline double np_sum_1d(const double *a, int n) {
 // is consumed by K5, so the pair geometry - noise hash, reciprocal square root - is evaluated once per tick instead
 // of twice.  HBM is the idle resource on this path (the kernels are issue / L1 bound), so 12 bytes per pair are a
 // good trade.
-template <typename Real>
+template <typename Real, int kNoise>  // kNoise: SC_NOISE_* resolved at compile time (no branch in the pair loop)
 __global__ void __launch_bounds__(SC_BLOCK)
 k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
           const double2 *__restrict__ pos, const float2 *__restrict__ rel, const uint32_t *__restrict__ cell_key,
@@ -217,7 +220,8 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
     pair_off[s] = off;
     pair_cnt[s] = (uint8_t)K;
     const uint32_t uid_s = uid[s];
-    const uint32_t nbase = (P.noise_mode == SC_NOISE_HOST) ? noise_off[rank_of_uid[uid_s]] : 0u;
+    uint32_t nbase = 0u;
+    if constexpr (kNoise == SC_NOISE_HOST) nbase = noise_off[rank_of_uid[uid_s]];
     Real ax = 0, ay = 0;
     Real psum = 0;
     double wl[sizeof(Real) == 8 ? SC_MAX_NEIGHBORS : 1];  // fp64 only: np.sum's pairwise order needs the list
@@ -230,13 +234,14 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
         const uint32_t j = e & SC_IDX_MASK;
         PairGeom<Real> pg;
         if constexpr (sizeof(Real) == 8) {
-            pg = pair_geom_f64(P, ps64, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+            pg = pair_geom_f64<kNoise>(P, ps64, pos[j], uid_s, uid[j], host_noise, nbase + (uint32_t)k);
         } else {
-            const int code = (int)(e >> 28);
+            const uint32_t cx = (e >> 28) & 3u, cy = e >> 30;  // (dc + 1), (dr + 1)
+            const float ox = cx == 0u ? -df : (cx == 2u ? df : 0.0f), oy = cy == 0u ? -df : (cy == 2u ? df : 0.0f);
             const float2 rj = rel[j];
-            const float rx = (rs.x - rj.x) - (float)(code % 3 - 1) * df;
-            const float ry = (rs.y - rj.y) - (float)(code / 3 - 1) * df;
-            pg = pair_geom_f32(P, rx, ry, uid_s, uid[j], host_noise, nbase + (uint32_t)k);
+            const float rx = (rs.x - rj.x) - ox;
+            const float ry = (rs.y - rj.y) - oy;
+            pg = pair_geom_f32<kNoise>(P, rx, ry, uid_s, uid[j], host_noise, nbase + (uint32_t)k);
         }
         pair_j[(size_t)off + k] = j;
         typename Vec2<Real>::type nv;
