@@ -73,8 +73,11 @@ __device__ __forceinline__ int collect_neighbors(uint32_t s, uint32_t c, const G
     {                                                                                                            \
         const float by = rs.y - (float)(DR) * df;                                                                \
         /* count < 20 in the loop condition = trim_collisions, collision_detector.py:91-93 */                   \
+        float2 rnext = rel[(FIRST) != (STOP) ? (FIRST) : s]; /* software pipelining: the load of candidate   */ \
         for (uint32_t j = (FIRST); j != (STOP) && count < SC_MAX_NEIGHBORS; j += (ASC) ? 1u : 0xFFFFFFFFu) {     \
-            const float2 rj = rel[j];                                                                            \
+            const float2 rj = rnext;                         /* j + 1 is in flight while j is being tested   */ \
+            const uint32_t jn = j + ((ASC) ? 1u : 0xFFFFFFFFu);                                                  \
+            rnext = rel[jn != (STOP) ? jn : s];                                                                  \
             /* x offset of the candidate's cell column relative to ours: (rel_j + (dc, dr) d) - rel_s */         \
             const float ox = (j >= (B2)) ? df : ((j >= (B1)) ? 0.0f : -df);                                      \
             const float dx = (rj.x + ox) - rs.x, dy = rj.y - by;                                                 \
@@ -209,14 +212,23 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
     NbrList lst{s_list + threadIdx.x};
     int K = 0;
     if (live) K = collect_neighbors(s, cell_key[s], g, cell_start, rel, pos, lst);
-    // the block's records go to one contiguous chunk of the pair buffer (one atomic per block; where the chunk
-    // lands is arbitrary, but it is only ever reached through pair_off, so results do not depend on it)
-    uint32_t total;
-    const uint32_t before = block_exclusive_scan((uint32_t)K, total);
-    if (threadIdx.x == 0) s_base = total ? atomicAdd(&cnt->pair_cursor, total) : 0u;
-    __syncthreads();
+    // the warp's records go to one contiguous chunk of the pair buffer (one atomic per warp, no block barrier: a
+    // __syncthreads here made every warp wait for the block's slowest neighbor scan).  Where the chunk lands is
+    // arbitrary, but it is only ever reached through pair_off, so results do not depend on it.
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = (uint32_t)K;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&cnt->pair_cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const uint32_t before = inc - (uint32_t)K;
     if (!live) return;
-    const uint32_t off = s_base + before;
+    const uint32_t off = base + before;
     pair_off[s] = off;
     pair_cnt[s] = (uint8_t)K;
     const uint32_t uid_s = uid[s];
