@@ -25,9 +25,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
-# algorithmic bytes per particle per launch, mixed layout
-ALGO_BYTES = {"prepass_wall_key": 20 + 4, "place": 12, "rank_gather": 4 + 28 + 32, "density": 16 + 4 + 4 + 12,
-              "force_integrate": 60}
+# algorithmic bytes per particle per kernel for the mixed layout (pos f64x2, vel f32x2, id, p, s,
+# cell id), each record moved once per kernel.  These are the figures `roofline.achieved` is computed from.
+SURVEY_BYTES = {"prepass_wall_key": 20, "place": 14, "rank_gather": 56, "density": 28, "force_integrate": 60}
+
+
+# What THIS design moves per particle per launch: the same accounting plus the records K4 hands
+# to K5 (12 bytes per directed pair, K = measured mean pairs per particle) and the packed (p, s) record.
+def algo_bytes(K):
+    return {
+        "prepass_wall_key": 16 + 4 + 4,                       # R pos; W key, slot
+        "place": 4 + 4 + 4,                                   # R key, slot; W index
+        "rank_gather": (4 + 4 + 16 + 8 + 4) + (16 + 8 + 8 + 4 + 4),   # R idx, key, pos, vel, uid; W pos, rel, vel, uid, key
+        "density": (8 + 4 + 4) + (16 + 4 + 1 + 12 * K),       # R rel, key, uid; W (p, s), pair offset/count, pair records
+        "force_integrate": (16 + 8 + 16 + 4 + 1 + 12 * K) + (16 + 8),  # R pos, vel, (p, s), offset/count, records; W pos, vel
+    }
 
 
 def peaks():
@@ -167,7 +179,8 @@ def cpu_baseline_sample(scene, budget_s=15.0):
     cores = O.num_threads()
     return {"value": n * ticks / el, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{scene} {n} particles x {ticks} ticks in {el:.1f}s, oracle/step_oracle.c, {cores} OpenMP threads "
-                      f"(neighbor search scalar)"}
+                      f"(neighbor search scalar).  The reference itself is pure Python: 6.1-7.0e3 particle-steps/s "
+                      f"on one core in the build container (BASELINE.md section 2); it cannot run on the GPU box."}
 
 
 def main():
@@ -283,6 +296,12 @@ def main():
     total_ms_prof, _, kernels = timed_pass(True)
     clocks = sampler.stop()
     n_live = ctx.particle_count() if dom is None else dom.status()["n_local"]
+    if dom is None:   # mean directed pairs per particle of the last tick (sizes the pair records in the byte model)
+        counts, _ = ctx.get_neighbors(n_live)
+        mean_pairs = float(counts.mean())
+        del counts
+    else:
+        mean_pairs = 5.3  # strip mode has no tap; rest-density value measured on one GPU
     dist_status = None if dom is None else dom.status()
 
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -336,10 +355,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
+        ALGO_BYTES = algo_bytes(mean_pairs)
         top = max((k for k in kernels if k in ALGO_BYTES), key=lambda k: kernels[k]["ms"], default="density")
         k = kernels.get(top, {"launches": 1, "ms": float("nan")})
         k_ms = k["ms"] / max(k["launches"], 1)
-        achieved = ALGO_BYTES[top] * n_live / (k_ms * 1e-3) / 1e9
+        achieved = SURVEY_BYTES[top] * n_live / (k_ms * 1e-3) / 1e9
+        design_achieved = ALGO_BYTES[top] * n_live / (k_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -348,8 +369,9 @@ def main():
         for name, v in kernels.items():
             ms = v["ms"] / max(v["launches"], 1)
             per_kernel[name] = {"ms": round(ms, 5), "launches_per_step": round(v["launches"] / a.steps, 2)}
-            if name in ALGO_BYTES:
-                per_kernel[name]["algo_gbs"] = round(ALGO_BYTES[name] * n_live / (ms * 1e-3) / 1e9, 1)
+            if name in SURVEY_BYTES:
+                per_kernel[name]["algo_gbs"] = round(SURVEY_BYTES[name] * n_live / (ms * 1e-3) / 1e9, 1)
+                per_kernel[name]["design_gbs"] = round(ALGO_BYTES[name] * n_live / (ms * 1e-3) / 1e9, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -369,7 +391,14 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_particle": ALGO_BYTES[top], "kernel_ms": k_ms},
+                         "algorithmic_bytes_per_particle": SURVEY_BYTES[top], "kernel_ms": k_ms,
+                         "note": "K4 is issue-bound, not HBM-bound (ncu: 61 % issue-active, 7 % DRAM; profiles/)",
+                         "design": {"bytes_per_particle": ALGO_BYTES[top], "achieved": design_achieved,
+                                    "frac": design_achieved / peak, "mean_pairs_per_particle": mean_pairs},
+                         "whole_step": {"survey_bytes_per_particle": 178,
+                                        "achieved": 178 * n_live / (total_ms_max / a.steps * 1e-3) / 1e9,
+                                        "design_bytes_per_particle": sum(ALGO_BYTES.values()),
+                                        "design_achieved": sum(ALGO_BYTES.values()) * n_live / (total_ms_max / a.steps * 1e-3) / 1e9}},
             "kernels": per_kernel,
             "wall_s_timed_region": wall,
             "ms_per_step_with_per_kernel_events": total_ms_prof / a.steps,

@@ -105,3 +105,23 @@ def test_synthetic_scenes(maker, n):
     cells = np.floor(pos / d).astype(np.int64)
     occ = np.unique(cells[:, 0] * 100000 + cells[:, 1], return_counts=True)[1]
     assert 1.5 < occ.mean() < 2.1
+
+
+def test_headless_runner_records_the_reference_trajectory(oracle_backend, tmp_path):
+    """sand_crate_b200.run: the display-less replacement of main.py / Playback."""
+    from sand_crate_b200 import run as runner
+    world, g = world_from_freerun("stirring_cup")
+    cfg = {"playback": {"save_recording": False, "ticks_to_record": 20, "recording_output_dir_path": ".",
+                        "screen_x": 10, "screen_y": 10},
+           "world": {"coefficients": world.coefficients, "particle_sources": world.particle_sources,
+                     "rigid_bodies": world.rigid_bodies}}
+    path = tmp_path / "cup.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    out = tmp_path / "run.npz"
+    summary = runner.run(path, every=5, out=out, quiet=True)
+    assert summary["ticks"] == 20 and summary["particles_final"] == len(g["pos_t20"])
+    frames = {t: (p, prs, seg) for t, p, prs, seg in runner.load_recording(out)}
+    assert sorted(frames) == [5, 10, 15, 20]
+    for t in (5, 20):
+        assert np.array_equal(frames[t][0], g[f"pos_t{t}"]) and np.array_equal(frames[t][1], g[f"pressure_t{t}"])
+        assert np.array_equal(frames[t][2], g[f"segments_t{t}"])
