@@ -120,6 +120,14 @@ int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int64_t P, cons
 /* pad_segments (geometry_utils.py:146-172): padded 2S x 4. */
 int sc_pad_segments(const double *segments, int S, double pad, double *padded);
 
+/* ---- ForceMonitor (utils/force_monitor.py:13-37) -------------------------------------------------------------- */
+/* With the monitor on, every tick also sums |dv| over the particles for each of the six sections the reference
+ * wraps in `force_monitor(...)` (crate.py:110-124): tension, gravity, pressure, viscosity, wall_bounce,
+ * continuous_collision.  sc_get_monitor returns the six sums and the particle count of the last tick; the mean and
+ * the reference's 0.8 decay are the caller's (sand_crate_b200/crate.py).  Synchronises. */
+int sc_set_monitor(sc_ctx *ctx, int on);
+int sc_get_monitor(sc_ctx *ctx, double *sum_dv, int64_t *n);
+
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 /* Per-kernel CUDA-event timing on the context's stream.  sc_profile_read returns, for each kernel slot, the
  * number of launches and the summed milliseconds since sc_profile_enable(ctx, 1). */

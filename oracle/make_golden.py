@@ -37,6 +37,7 @@ STEP_TICKS = {
     "stirring_cup": [1, 20, 60, 150, 199, 260, 400],
     "wave_machine": [5, 100, 300, 500],
 }
+MONITOR_SECTIONS = ("tension", "gravity", "pressure", "viscosity", "wall_bounce", "continuous_collision")
 FREERUN_TICKS = {
     "stirring_cup": [1, 5, 20, 40, 80],
     "wave_machine": [1, 5, 20, 40],
@@ -67,6 +68,8 @@ def record_config(ref, name, quick):
             free[f"vel_t{tick}"] = rc.crate.particle_velocities.copy()
             free[f"segments_t{tick}"] = rc.crate.segments.copy()
             free[f"pressure_t{tick}"] = np.asarray(rc.crate.particles_pressure, dtype=np.float64).copy()
+            fm = rc.crate.force_monitor.context_to_velocity  # utils/force_monitor.py: EMA of mean |dv| per section
+            free[f"monitor_t{tick}"] = np.array([float(fm[k]) for k in MONITOR_SECTIONS])
         if tick % 50 == 0:
             print(f"  {name}: tick {tick}/{last}  P={rc.crate.particle_count}  {time.time() - t0:.0f}s", flush=True)
     world = {"coefficients": cfg.world_config.coefficients, "particle_sources": cfg.world_config.particle_sources,

@@ -49,7 +49,7 @@ def lib():
         L.oc_detect_particle_collisions.argtypes = [dp, C.c_int64, C.c_double, lp, lp, ip, ip]
         L.oc_detect_particle_collisions.restype = C.c_int
         L.oc_step.argtypes = [C.POINTER(Params), C.c_int64, dp, dp, dp, C.c_int, ip, dp, C.c_int, C.c_int, dp,
-                              C.c_uint64, C.POINTER(C.c_uint32), dp, ip, ip, dp, dp, dp, ip]
+                              C.c_uint64, C.POINTER(C.c_uint32), dp, ip, ip, dp, dp, dp, ip, dp]
         L.oc_step.restype = C.c_int
         L.oc_remove_particles.argtypes = [dp, dp, C.c_int64, C.c_double, C.POINTER(C.c_uint8)]
         L.oc_remove_particles.restype = C.c_int64
@@ -155,6 +155,7 @@ def step(coeffs, pos, vel, segments, body_len, body_kin, noise_mode=0, noise=Non
         out["tension_vec"] = np.zeros((P, 2))
         out["ccd_factor"] = np.ones(P)
         out["wall_count"] = np.zeros(P, np.int32)
+        out["force_monitor"] = np.zeros(6)
     if noise is not None:
         noise = np.ascontiguousarray(noise, dtype=np.float64)
     if uid is not None:
@@ -164,7 +165,7 @@ def step(coeffs, pos, vel, segments, body_len, body_kin, noise_mode=0, noise=Non
                        uid.ctypes.data_as(C.POINTER(C.c_uint32)) if uid is not None else None,
                        _dp(out.get("pos_search")), _ip(out.get("nbr_count")), _ip(out.get("nbr_idx_padded")),
                        _dp(out.get("pressure")), _dp(out.get("tension_vec")), _dp(out.get("ccd_factor")),
-                       _ip(out.get("wall_count")))
+                       _ip(out.get("wall_count")), _dp(out.get("force_monitor")))
     if rc:
         raise MemoryError("oracle allocation failed")
     out["pos_out"] = pos

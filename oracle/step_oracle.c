@@ -278,12 +278,13 @@ typedef struct {
  *                    np.random.rand stream (crate.py:168-170)
  *   uid           P ids for noise_mode 1 (NULL -> index)
  * optional outputs (may be NULL): pos_search (P x 2, after W2), counts/idx (P, P x 20), pressure (P),
- *   tension_vec (P x 2), ccd_factor (P), wall_count (P)
+ *   tension_vec (P x 2), ccd_factor (P), wall_count (P), monitor (6)
  */
 int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const double *segments, int S,
             const int32_t *body_len, const double *body_kin, int nbodies, int noise_mode, const double *noise,
             uint64_t tick_key, const uint32_t *uid, double *pos_search, int32_t *counts_out, int32_t *idx_out,
-            double *pressure_out, double *tension_out, double *ccd_out, int32_t *wall_count_out) {
+            double *pressure_out, double *tension_out, double *ccd_out, int32_t *wall_count_out,
+            double *monitor_out /* 6: mean |dv| per force section, utils/force_monitor.py:27-33 */) {
     const double dt = prm->dt, r = prm->radius;
     const double d = r * 2; /* crate.py:65-67 */
     if (P == 0) return 0;
@@ -420,11 +421,14 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
     double *padded = (double *)malloc(sizeof(double) * 8 * (size_t)(S ? S : 1));
     oc_pad_segments(segments, S, r, padded); /* crate.py:182 */
 
-#pragma omp parallel for schedule(static)
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0, m5 = 0;
+#define OC_STAGE(ACC) { const double ex_ = vx - mvx_, ey_ = vy - mvy_; ACC += sqrt(ex_ * ex_ + ey_ * ey_); mvx_ = vx; mvy_ = vy; }
+#pragma omp parallel for schedule(static) reduction(+ : m0, m1, m2, m3, m4, m5)
     for (int64_t i = 0; i < P; ++i) {
         const int K = counts[i];
         const int V = wall_n[i];
         double vx = vel[2 * i], vy = vel[2 * i + 1];
+        double mvx_ = vx, mvy_ = vy;
         const double pi_ = p[i];
         /* ---- F3 pass 2 crate.py:343-353 ---- */
         if (K > 0) {
@@ -441,8 +445,10 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
             }
             vx += dt * ax; vy += dt * ay;
         }
+        OC_STAGE(m0)
         /* ---- F4 apply_gravity crate.py:309-310 ---- */
         vx += dt * prm->gx; vy += dt * prm->gy;
+        OC_STAGE(m1)
         /* ---- F5 apply_pressure crate.py:295-307: real rows then virtual rows (p_k = 0, n_k = vc_k) ---- */
         if (K + V > 0) {
             double ax = 0, ay = 0;
@@ -461,6 +467,7 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
             const double c = dt * prm->pressure_amplifier;
             vx += c * ax; vy += c * ay;
         }
+        OC_STAGE(m2)
         /* ---- F6 apply_viscosity crate.py:316-323: snapshot v_j, CURRENT v_i; runs for every particle ---- */
         {
             double ax = 0, ay = 0;
@@ -472,6 +479,7 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
             const double c = dt * prm->viscosity;
             vx += c * ax; vy += c * ay;
         }
+        OC_STAGE(m3)
         /* ---- B1 apply_wall_bounce crate.py:245-259 ---- */
         if (V > 0) {
             double sx_ = 0, sy_ = 0, ux = 0, uy = 0;
@@ -495,6 +503,7 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
                 vx += cx * prm->wall_collision_decay; vy += cy * prm->wall_collision_decay;
             }
         }
+        OC_STAGE(m4)
         /* ---- B2 apply_continuous_collision_velocity_fix crate.py:177-200 ---- */
         {
             const double ax_ = pos[2 * i], ay_ = pos[2 * i + 1];
@@ -519,7 +528,13 @@ int oc_step(const oc_params *prm, int64_t P, double *pos, double *vel, const dou
             if (ccd_out) ccd_out[i] = f;
             vx *= f; vy *= f;
         }
+        OC_STAGE(m5)
         vel[2 * i] = vx; vel[2 * i + 1] = vy;
+    }
+#undef OC_STAGE
+    if (monitor_out) {
+        monitor_out[0] = m0 / (double)P; monitor_out[1] = m1 / (double)P; monitor_out[2] = m2 / (double)P;
+        monitor_out[3] = m3 / (double)P; monitor_out[4] = m4 / (double)P; monitor_out[5] = m5 / (double)P;
     }
     /* ---- I apply_particles_velocity crate.py:360-361 ---- */
     for (int64_t i = 0; i < 2 * P; ++i) pos[i] += dt * vel[i];

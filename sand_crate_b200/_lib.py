@@ -77,6 +77,8 @@ SIGNATURES = {
     "sc_dist_get_owned": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64, _lp]),
     "sc_dist_status": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
     "sc_set_state_uids": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64]),
+    "sc_set_monitor": (C.c_int, [_ctx, C.c_int]),
+    "sc_get_monitor": (C.c_int, [_ctx, _dp, _lp]),
     "sc_profile_enable": (C.c_int, [_ctx, C.c_int]),
     "sc_profile_read": (C.c_int, [_ctx, _lp, _dp, C.c_int]),
     "sc_profile_name": (C.c_char_p, [C.c_int]),
@@ -308,6 +310,17 @@ class Context:
         self._ck(self._L.sc_dist_status(self._h, self._devptr(send_lo), self._devptr(send_hi),
                                         C.byref(ov), C.byref(far), C.byref(n)))
         return {"overflow": bool(ov.value), "too_far": bool(far.value), "n_local": n.value}
+
+    # ---- ForceMonitor ----
+    def set_monitor(self, on: bool = True):
+        self._ck(self._L.sc_set_monitor(self._h, int(on)))
+
+    def get_monitor(self):
+        """(sum over particles of |dv| for the six force sections, particle count) of the last tick."""
+        sums = np.zeros(6)
+        n = C.c_int64()
+        self._ck(self._L.sc_get_monitor(self._h, _ptr(sums, _dp), C.byref(n)))
+        return sums, n.value
 
     # ---- measurement ----
     def profile_enable(self, on: bool = True):

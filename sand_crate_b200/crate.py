@@ -31,10 +31,61 @@ _PRECISIONS = {"f64": _lib.PRECISION_F64, "mixed": _lib.PRECISION_MIXED}
 _NOISES = {"reference": _lib.NOISE_HOST, "counter": _lib.NOISE_COUNTER, "none": _lib.NOISE_NONE}
 
 
+FORCE_SECTIONS = ("tension", "gravity", "pressure", "viscosity", "wall_bounce", "continuous_collision")
+
+
+class ForceMonitor:
+    """The reference's diagnostic overlay (utils/force_monitor.py:13-37): per force section of the tick
+    (crate.py:110-124) an exponential moving average, decay 0.8, of the mean |dv| the section caused.  The six sums
+    come from the force kernel's monitor mode (`sc_set_monitor`); enabling it costs six atomics per particle."""
+
+    DECAY = 0.80
+
+    def __init__(self) -> None:
+        self.context_to_velocity: dict = {}
+
+    def update(self, sums, count: int) -> None:
+        if count == 0:  # force_monitor.py:28-29
+            return
+        for name, total in zip(FORCE_SECTIONS, sums):
+            prev = self.context_to_velocity.get(name, 0)
+            self.context_to_velocity[name] = prev * self.DECAY + (1 - self.DECAY) * (total / count)
+
+    def report(self) -> str:
+        rounded = {name: float(f"{1000 * v:.1f}") for name, v in self.context_to_velocity.items()}
+        return yaml.dump({"Forces": rounded})
+
+
+class KernelTimer:
+    """Counterpart of the reference's `Timer` (utils/timer.py:10-48): per section an exponential moving average,
+    decay 0.9, of its duration - here the sections are the tick's kernels, timed with CUDA events on the stream."""
+
+    DECAY = 0.9
+
+    def __init__(self) -> None:
+        self.durations: dict = {}
+        self._seen: dict = {}
+
+    def update(self, totals: dict) -> None:
+        for name, rec in totals.items():
+            launches, ms = self._seen.get(name, (0, 0.0))
+            if rec["launches"] > launches:
+                dur = (rec["ms"] - ms) / (rec["launches"] - launches) * 1e-3
+                self.durations[name] = self.durations.get(name, 0) * self.DECAY + (1 - self.DECAY) * dur
+            self._seen[name] = (rec["launches"], rec["ms"])
+
+    def report(self) -> str:
+        frame = sum(self.durations.values())
+        if frame <= 0:
+            return yaml.dump({"Timing": {}, "FPS": "n/a"})
+        rows = {k: f"{1e6 * v:.0f} us ({100 * v / frame:.0f}%)" for k, v in self.durations.items()}
+        return yaml.dump({"Timing": rows, "FPS": f"{int(1 / frame)} ({1e3 * frame:.3f} ms)"})
+
+
 class Crate:
     def __init__(self, world_config: WorldConfig, *, precision: str = "f64", noise: str = "reference",
                  device: int = 0, noise_seed: int = 0, capacity: int | None = None, stream: int | None = None,
-                 profile: bool = False) -> None:
+                 profile: bool = False, monitor: bool = False) -> None:
         np.random.seed(0)  # crate.py:22 - sources and reference-mode noise share this global stream
         self.tick: int = 0
         self.debug_arrows: list = []
@@ -52,7 +103,9 @@ class Crate:
             raise ValueError(f"noise must be one of {sorted(_NOISES)}")
         self.precision, self.noise = precision, noise
         self._noise_seed = int(noise_seed)
-        self._device, self._stream, self._profile = device, stream, profile
+        self._device, self._stream, self._profile, self._monitor = device, stream, profile, monitor
+        self.force_monitor = ForceMonitor()
+        self.debug_timer = KernelTimer()
         cap = int(capacity if capacity is not None else max(int(getattr(self, "max_particles", 0) or 0), 1))
         self._ctx = None
         self._open_context(cap)
@@ -66,6 +119,8 @@ class Crate:
         self._ctx.set_noise(_NOISES[self.noise], self._noise_seed)
         if self._profile:
             self._ctx.profile_enable(True)
+        if self._monitor:
+            self._ctx.set_monitor(True)
 
     def _ensure_capacity(self, needed: int) -> None:
         if needed <= self._ctx.capacity:
@@ -154,6 +209,10 @@ class Crate:
         self.apply_gravity_to_free_bodies()
         self._cache = {}
         self.tick += 1
+        if self._monitor:
+            self.force_monitor.update(*self._ctx.get_monitor())
+        if self._profile:
+            self.debug_timer.update(self._ctx.profile_read())
 
     def create_new_particles(self) -> None:  # crate.py:138-147
         for source in self.particle_sources:
@@ -197,8 +256,9 @@ class Crate:
         """Built on demand so a headless run never synchronises for the overlay."""
         text = f"Tick: {self.tick}\nParticles: {self.particle_count}\n"
         if self._profile:
-            self._kernel_ms = self._ctx.profile_read()
-            text += yaml.dump({k: round(v["ms"] / max(v["launches"], 1), 4) for k, v in self._kernel_ms.items()})
+            text += self.debug_timer.report()
+        if self._monitor:
+            text += f"\n\n{self.force_monitor.report()}"
         text += f"\n\n{self.get_coefficient_debug()}"
         return text
 

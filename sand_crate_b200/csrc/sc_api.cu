@@ -62,6 +62,8 @@ struct sc_ctx {
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
     bool lists_valid = false, rank_valid = false;
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
+    bool monitor_on = false;  // ForceMonitor mode: K5 also sums |dv| per force stage
+    double *monitor = nullptr; // 6 sums + particle count of the last tick
     bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
     DistCfg dist{};
     WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers (+ push completion counters)
@@ -270,7 +272,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
                     c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
-                    c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy};
+                    c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy, c->monitor};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : c->pool) cudaEventDestroy(e);
@@ -613,6 +615,21 @@ static int launch_density(sc_ctx *ctx, const Grid &g, const DevParams &dp, const
     return 0;
 }
 
+template <typename Real>
+static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n) {
+    typedef typename Vec2<Real>::type R2;
+    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    ProfScope ps(ctx, SLOT_FORCE);
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
+                          (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
+                          (const PS<Real> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre,
+                          ctx->pos_cur, (R2 *)ctx->vel_cur, ctx->monitor);
+    };
+    CK(ctx->monitor_on ? go(k_force<Real, true>) : go(k_force<Real, false>));
+    return 0;
+}
+
 static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
     const int64_t n = ctx->n_host;
     const Grid &g = ctx->grid;
@@ -627,21 +644,13 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 CKR(launch_density<double>(ctx, g, dp, noise_off, n));
             }
-            ProfScope ps(ctx, SLOT_FORCE);
-            CK(launch_pdl(k_force<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                n_ptr, dp, ctx->walls, ctx->pos_srt, (const double2 *)ctx->vel_srt, ctx->pair_j,
-                (const double2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<double> *)ctx->ps,
-                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (double2 *)ctx->vel_cur));
+            CKR(launch_force<double>(ctx, dp, n_ptr, n));
         } else {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 CKR(launch_density<float>(ctx, g, dp, noise_off, n));
             }
-            ProfScope ps(ctx, SLOT_FORCE);
-            CK(launch_pdl(k_force<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                n_ptr, dp, ctx->walls, ctx->pos_srt, (const float2 *)ctx->vel_srt, ctx->pair_j,
-                (const float2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps,
-                ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur));
+            CKR(launch_force<float>(ctx, dp, n_ptr, n));
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
@@ -948,6 +957,30 @@ extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int6
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
     cudaFree(dp); cudaFree(ds); cudaFree(dn); cudaFree(dd);
+    return 0;
+}
+
+// ---- ForceMonitor (utils/force_monitor.py) ------------------------------------------------------------------------
+extern "C" int sc_set_monitor(sc_ctx *ctx, int on) {
+    if (!ctx) return fail(ctx, "sc_set_monitor: NULL ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (on && !ctx->monitor) {
+        CKR(dev_alloc(ctx, &ctx->monitor, 8));
+        CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    }
+    ctx->monitor_on = on != 0;
+    return 0;
+}
+
+extern "C" int sc_get_monitor(sc_ctx *ctx, double *sum_dv, int64_t *n) {
+    if (!ctx || !sum_dv) return fail(ctx, "sc_get_monitor: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->monitor) return fail(ctx, "sc_get_monitor: sc_set_monitor(ctx, 1) has not been called");
+    double h[8];
+    CK(cudaMemcpyAsync(h, ctx->monitor, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int q = 0; q < 6; ++q) sum_dv[q] = h[q];
+    if (n) *n = (int64_t)h[6];
     return 0;
 }
 

@@ -278,7 +278,9 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
 
 // ------------------------------------------------------------------------------------------------------------
 // K5: all forces, wall bounce, continuous collision and integration for particle s
-template <typename Real>
+// kMonitor: also accumulate, per force stage, the sum over particles of |dv| (the reference's ForceMonitor,
+// utils/force_monitor.py:23-33, wraps exactly these six stages: crate.py:110-124)
+template <typename Real, bool kMonitor>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
         const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
@@ -286,11 +288,21 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         const uint32_t *__restrict__ pair_off, const uint8_t *__restrict__ pair_cnt,
         const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
         const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
-        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out) {
+        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out,
+        double *__restrict__ monitor) {
     pdl_enter();
     typedef typename Vec2<Real>::type R2;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
+    double mon[6] = {0, 0, 0, 0, 0, 0};
+    double mpx = 0, mpy = 0;  // velocity before the current stage
+    auto stage = [&](int q, double cx, double cy) {
+        if constexpr (kMonitor) {
+            const double ex = cx - mpx, ey = cy - mpy;
+            mon[q] = sqrt(ex * ex + ey * ey);  // np.linalg.norm(velocity_diff, axis=1)
+            mpx = cx; mpy = cy;
+        }
+    };
     const double2 ps = pos[s];
     const PS<Real> me = ps_in[s];
     const Real p_i = me.p;
@@ -376,12 +388,16 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
 
     const Real dt = (Real)P.dt;
     Real vx = v0.x, vy = v0.y;
+    if constexpr (kMonitor) { mpx = (double)vx; mpy = (double)vy; }
     if (K > 0) { vx += dt * tx; vy += dt * ty; }                       // F3, crate.py:352
+    stage(0, (double)vx, (double)vy);
     vx += (Real)(P.dt * P.gx); vy += (Real)(P.dt * P.gy);               // F4, crate.py:310
+    stage(1, (double)vx, (double)vy);
     if (K + V > 0) {                                                     // F5, crate.py:297, 306
         const Real c = (Real)(P.dt * P.amp);
         vx += c * qx; vy += c * qy;
     }
+    stage(2, (double)vx, (double)vy);
     {                                                                    // F6, crate.py:319-323
         Real ax = 0, ay = 0;
         if constexpr (sizeof(Real) == 8) {
@@ -397,6 +413,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         const Real c = (Real)(P.dt * P.visc);
         vx += c * ax; vy += c * ay;
     }
+    stage(3, (double)vx, (double)vy);
     double dvx = (double)vx, dvy = (double)vy;
     if (V > 0) {                                                         // B1, crate.py:245-259
         const double Nx = wnx / (double)V, Ny = wny / (double)V;
@@ -411,6 +428,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
             dvx += cx * P.decay; dvy += cy * P.decay;
         }
     }
+    stage(4, dvx, dvy);
     {                                                                    // B2, crate.py:177-200
         const double mvx = dvx * P.dt, mvy = dvy * P.dt;
         const double bx = ps.x + mvx, by = ps.y + mvy;
@@ -437,6 +455,12 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
             }
         }
         dvx *= f; dvy *= f;
+    }
+    stage(5, dvx, dvy);
+    if constexpr (kMonitor) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) atomicAdd(&monitor[q], mon[q]);  // diagnostic mode only: speed is irrelevant
+        if (threadIdx.x == 0 && blockIdx.x == 0) monitor[6] = (double)*n_ptr;
     }
     R2 vo;
     vo.x = (Real)dvx; vo.y = (Real)dvy;

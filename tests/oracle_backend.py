@@ -40,6 +40,12 @@ class OracleContext:
     def profile_enable(self, on=True):
         pass
 
+    def set_monitor(self, on=True):
+        self.monitor = None
+
+    def get_monitor(self):
+        return self.monitor * len(self.prs), len(self.prs)
+
     def profile_read(self):
         return {}
 
@@ -87,6 +93,7 @@ class OracleContext:
         out = O.step(self._coeffs(), self.pos, self.vel, seg, bl, bk, noise_mode=mode, noise=noise,
                      tkey=O.tick_key(self.seed, self.tick), uid=self.uid & np.uint32(0x7FFFFFFF))
         self.pos, self.vel, self.prs = out["pos_out"], out["vel_out"], out["pressure"]
+        self.monitor = out["force_monitor"]
         self.tick += 1
         self._pending = None
 

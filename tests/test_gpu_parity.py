@@ -335,3 +335,18 @@ def test_strips_two_gpus_bit_identical_to_single_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert res.stdout.count("bit-identical to single GPU = True") == 3, res.stdout
+
+
+def test_force_monitor_on_gpu_matches_reference():
+    """The force kernel's monitor mode (sc_set_monitor) reproduces the reference's ForceMonitor overlay."""
+    from sand_crate_b200.crate import FORCE_SECTIONS
+    world, g = world_from_freerun("wave_machine")
+    crate = Crate(world, monitor=True, profile=True)
+    for tick in range(1, 41):
+        crate.physics_tick()
+        if f"monitor_t{tick}" in g.files:
+            got = np.array([crate.force_monitor.context_to_velocity[k] for k in FORCE_SECTIONS])
+            assert np.allclose(got, g[f"monitor_t{tick}"], rtol=1e-10, atol=1e-15), tick
+            assert np.array_equal(crate.particles, g[f"pos_t{tick}"])  # monitor mode does not change the physics
+    text = crate.debug_prints
+    assert "Forces" in text and "Timing" in text and "force_integrate" in text

@@ -125,3 +125,16 @@ def test_headless_runner_records_the_reference_trajectory(oracle_backend, tmp_pa
     for t in (5, 20):
         assert np.array_equal(frames[t][0], g[f"pos_t{t}"]) and np.array_equal(frames[t][1], g[f"pressure_t{t}"])
         assert np.array_equal(frames[t][2], g[f"segments_t{t}"])
+
+
+@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40)])
+def test_force_monitor_overlay_matches_reference(oracle_backend, name, last):
+    """ForceMonitor (utils/force_monitor.py): EMA of the mean |dv| per force section, against the reference's own."""
+    world, g = world_from_freerun(name)
+    crate = Crate(world, monitor=True)
+    for tick in range(1, last + 1):
+        crate.physics_tick()
+        if f"monitor_t{tick}" in g.files:
+            got = np.array([crate.force_monitor.context_to_velocity[k] for k in crate_mod.FORCE_SECTIONS])
+            assert np.allclose(got, g[f"monitor_t{tick}"], rtol=1e-11, atol=1e-15), tick
+    assert "Forces" in crate.debug_prints and "tension" in crate.force_monitor.report()
