@@ -36,11 +36,13 @@ from oracle.ref_shim import RecordingCrate, load_reference  # noqa: E402
 STEP_TICKS = {
     "stirring_cup": [1, 20, 60, 150, 199, 260, 400],
     "wave_machine": [5, 100, 300, 500],
+    "free_body": [],
 }
 MONITOR_SECTIONS = ("tension", "gravity", "pressure", "viscosity", "wall_bounce", "continuous_collision")
 FREERUN_TICKS = {
     "stirring_cup": [1, 5, 20, 40, 80],
     "wave_machine": [1, 5, 20, 40],
+    "free_body": [1, 10, 30, 60],
 }
 
 
@@ -51,8 +53,20 @@ def save(name, **arrays):
     print(f"  wrote {name}  ({os.path.getsize(path) / 1024:.0f} KiB)", flush=True)
 
 
+def free_body_config(ref):
+    """wave_machine with its motored paddle replaced by a FREE body (rigid_body.py:18-49, "free" in
+    BODY_TYPE_TO_CLASS): a bar that falls under gravity (crate.py:311-314) and spins - the one body type neither
+    shipped config exercises."""
+    cfg = ref.load_config(os.path.join(ref.config_dir, "wave_machine.yaml"))
+    bodies = [b for b in cfg.world_config.rigid_bodies if "fixed" in b]
+    bodies.append({"free": {"name": "bar", "segments": [[[-0.15, 0.0], [0.15, 0.0]], [[0.0, -0.05], [0.0, 0.05]]],
+                            "position": [0.3, 0.75], "angular_clockwise_velocity": 0.8}})
+    cfg.world_config.rigid_bodies = bodies
+    return cfg
+
+
 def record_config(ref, name, quick):
-    cfg = ref.load_config(os.path.join(ref.config_dir, f"{name}.yaml"))
+    cfg = free_body_config(ref) if name == "free_body" else ref.load_config(os.path.join(ref.config_dir, f"{name}.yaml"))
     rc = RecordingCrate(cfg.world_config)
     step_ticks = [t for t in STEP_TICKS[name] if not (quick and t > 100)]
     free_ticks = FREERUN_TICKS[name]
@@ -142,7 +156,7 @@ def main():
         neighbor_cases(ref)
     if a.only in ("", "geometry"):
         geometry_cases(ref)
-    for name in ("stirring_cup", "wave_machine"):
+    for name in ("stirring_cup", "wave_machine", "free_body"):
         if a.only in ("", name):
             print(f"recording {name}", flush=True)
             record_config(ref, name, a.quick)

@@ -129,7 +129,7 @@ def test_step_no_noise_bit_exact():
 
 
 # ---- the drop-in object, whole runs ---------------------------------------------------------------------------
-@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40)])
+@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40), ("free_body", 60)])
 def test_crate_free_run_bit_exact(name, last):
     """`Crate(world_config).physics_tick()` x N == the reference's trajectory, bit for bit (fp64 + reference RNG)."""
     world, g = world_from_freerun(name)

@@ -55,7 +55,7 @@ def test_rigid_bodies_follow_the_reference(name):
             assert np.array_equal(seg, g[f"segments_t{tick}"]), tick
 
 
-@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40)])
+@pytest.mark.parametrize("name,last", [("stirring_cup", 80), ("wave_machine", 40), ("free_body", 60)])
 def test_crate_protocol_reproduces_reference_trajectory(oracle_backend, name, last):
     """Sources + RNG protocol + body motion + removal, whole run, bit for bit (step = oracle test double)."""
     world, g = world_from_freerun(name)
