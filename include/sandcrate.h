@@ -170,6 +170,12 @@ int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int6
  * number of local particles (owned + ghosts).  Synchronises. */
 int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *send_hi_dev, int *overflow, int *too_far,
                    int64_t *n_local);
+/* Re-balancing the partition.  sc_dist_row_histogram: number of OWNED particles per cell row, rows row0 .. row0 +
+ * nrows - 1 (outliers clamped to the ends); the caller sums it over the ranks (the only collective of the scheme, on
+ * re-cut ticks only) and derives new cuts.  sc_dist_set_rows moves this rank's cuts; a cut may move by less than
+ * `halo_rows` rows per tick - the rows it hands over then travel as ordinary migrants of the next sc_dist_pack. */
+int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, uint64_t *hist);
+int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi);
 /* like sc_set_state but with caller-chosen uids (global particle ids of a partitioned scene) */
 int sc_set_state_uids(sc_ctx *ctx, const double *pos, const double *vel, const uint32_t *uid, int64_t n);
 

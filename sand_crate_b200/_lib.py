@@ -76,6 +76,8 @@ SIGNATURES = {
     "sc_dist_unpack_flagged": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_get_owned": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64, _lp]),
     "sc_dist_status": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
+    "sc_dist_row_histogram": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
+    "sc_dist_set_rows": (C.c_int, [_ctx, C.c_int64, C.c_int64]),
     "sc_set_state_uids": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64]),
     "sc_set_monitor": (C.c_int, [_ctx, C.c_int]),
     "sc_get_monitor": (C.c_int, [_ctx, _dp, _lp]),
@@ -297,6 +299,14 @@ class Context:
         lo, hi = lo or (None, None), hi or (None, None)
         self._ck(self._L.sc_dist_unpack_flagged(self._h, *[self._devptr(x) for x in lo],
                                                 *[self._devptr(x) for x in hi], C.c_uint32(value)))
+
+    def dist_row_histogram(self, row0: int, nrows: int):
+        hist = np.zeros(nrows, np.uint64)
+        self._ck(self._L.sc_dist_row_histogram(self._h, int(row0), int(nrows), hist.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return hist
+
+    def dist_set_rows(self, row_lo: int, row_hi: int):
+        self._ck(self._L.sc_dist_set_rows(self._h, int(row_lo), int(row_hi)))
 
     def dist_get_owned(self):
         cap = self.capacity

@@ -183,6 +183,8 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
 static void refresh_wall_boxes(sc_ctx *ctx);
 static int sync_count(sc_ctx *ctx);
 
+#define SC_DIST_ROW_SLACK 96
+
 // Cell grid of the world box; in strip mode only the rows this rank can ever hold (its strip, the halo, and the
 // one-row shift the wall fix can add), so clearing and scanning the grid scales with the strip, not the scene.
 static int world_grid(sc_ctx *ctx) {
@@ -191,7 +193,8 @@ static int world_grid(sc_ctx *ctx) {
     const int lo = (int)std::floor((-2 * r) / d) - 1, hi = (int)std::floor((1 + 2 * r) / d) + 1;
     int rlo = lo, rhi = hi;
     if (ctx->dist_on) {
-        const long long margin = ctx->dist.halo + 2;
+        // halo + wall-fix shift + slack for cuts that slide while the partition is re-balanced (sc_dist_set_rows)
+        const long long margin = ctx->dist.halo + 2 + SC_DIST_ROW_SLACK;
         if (ctx->dist.has_lo && ctx->dist.row_lo - margin > rlo) rlo = (int)(ctx->dist.row_lo - margin);
         if (ctx->dist.has_hi && ctx->dist.row_hi + margin < rhi) rhi = (int)(ctx->dist.row_hi + margin);
     }
@@ -1045,6 +1048,57 @@ extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_
 }
 
 __global__ void k_set_count(Counters *cnt) { cnt->n = cnt->n_tmp; }
+
+extern "C" int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi) {
+    CKR(dist_ready(ctx, "sc_dist_set_rows"));
+    if (ctx->dist.has_lo && ctx->dist.has_hi && row_hi - row_lo < 2 * (int64_t)ctx->dist.halo)
+        return fail(ctx, "sc_dist_set_rows: a strip must be at least 2 * halo_rows high");
+    ctx->dist.row_lo = row_lo; ctx->dist.row_hi = row_hi;
+    // the restricted cell grid must still cover the strip, its halo and the wall-fix shift
+    const long long need = ctx->dist.halo + 2;
+    const long long g_lo = (long long)ctx->grid.row_min + 1, g_hi = (long long)ctx->grid.row_min + ctx->grid.nrows - 2;
+    const bool lo_ok = !ctx->dist.has_lo || row_lo - need >= g_lo, hi_ok = !ctx->dist.has_hi || row_hi + need <= g_hi;
+    if (!lo_ok || !hi_ok) {
+        // the world grid is a superset check: rows of the world box are always inside (world_grid clamps to them)
+        const double d = ctx->dp.d, r = ctx->dp.r;
+        const long long w_lo = (long long)std::floor((-2 * r) / d) - 1, w_hi = (long long)std::floor((1 + 2 * r) / d) + 1;
+        if ((ctx->dist.has_lo && row_lo - need < g_lo && g_lo > w_lo) ||
+            (ctx->dist.has_hi && row_hi + need > g_hi && g_hi < w_hi)) {
+            CKR(sync_count(ctx));
+            CKR(world_grid(ctx));
+            ctx->n_host = ctx->cap;
+            ctx->n_exact = false;
+        }
+    }
+    return 0;
+}
+
+extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, uint64_t *hist) {
+    CKR(dist_ready(ctx, "sc_dist_row_histogram"));
+    if (nrows < 1 || nrows > (1 << 24) || !hist) return fail(ctx, "sc_dist_row_histogram: bad arguments");
+    if (ctx->carry_count) {
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
+        ctx->carry_count = false;
+    }
+    unsigned long long *d_hist = nullptr;
+    CK(cudaMalloc((void **)&d_hist, sizeof(unsigned long long) * (size_t)nrows));
+    CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (size_t)nrows, ctx->stream));
+    const int64_t n = ctx->n_host;
+    if (n > 0) {
+        ProfScope ps(ctx, SLOT_IO);
+        if (ctx->precision == SC_PRECISION_F64)
+            k_dist_row_hist<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
+                                                                             ctx->uid_cur, row0, (int)nrows, d_hist);
+        else
+            k_dist_row_hist<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
+                                                                            ctx->uid_cur, row0, (int)nrows, d_hist);
+    }
+    CK(cudaMemcpyAsync(hist, d_hist, sizeof(uint64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d_hist));
+    return 0;
+}
 
 extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     CKR(dist_ready(ctx, "sc_dist_pack"));

@@ -168,6 +168,20 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
     }
 }
 
+// per-row counts of the owned particles (input of the partition re-cut): hist[row - row0], rows outside are clamped
+template <typename Real>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_dist_row_hist(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__restrict__ pos,
+                const uint32_t *__restrict__ uid, long long row0, int nrows, unsigned long long *__restrict__ hist) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_ptr) return;
+    if (uid[i] & SC_GHOST_BIT) return;
+    const double fr = floor_div(pos[i].y, g);
+    long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
+    row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
+    atomicAdd(&hist[row - row0], 1ull);
+}
+
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b, uint32_t *n_out) {
     a->count = 0; a->overflow = 0; a->too_far = 0; a->pad_ = 0;
     b->count = 0; b->overflow = 0; b->too_far = 0; b->pad_ = 0;

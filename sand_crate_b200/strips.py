@@ -52,6 +52,22 @@ def partition_rows(rows: np.ndarray, nranks: int, halo_rows: int = HALO_ROWS) ->
     return cuts
 
 
+def cuts_from_histogram(hist: np.ndarray, row0: int, nranks: int, halo_rows: int = HALO_ROWS) -> list[int]:
+    """The same equal-count cuts as `partition_rows`, from a per-row particle histogram starting at row `row0`."""
+    if nranks == 1:
+        return [INT64_MIN, INT64_MAX]
+    cum = np.cumsum(hist.astype(np.int64))
+    cuts = [INT64_MIN]
+    prev = row0
+    for k in range(1, nranks):
+        r = row0 + int(np.searchsorted(cum, cum[-1] * k / nranks, side="left")) + 1
+        r = max(r, prev + 2 * halo_rows)
+        cuts.append(r)
+        prev = r
+    cuts.append(INT64_MAX)
+    return cuts
+
+
 class StripDomain:
     """One rank's share of a strip-decomposed scene.
 
@@ -61,7 +77,8 @@ class StripDomain:
     def __init__(self, world, pos, vel, *, rank: int, world_size: int, precision: str = "mixed",
                  noise: str = "counter", noise_seed: int = 0, device: int = 0, stream: int | None = None,
                  halo_rows: int = HALO_ROWS, slack: float = 1.3, wire_capacity: int | None = None,
-                 context_factory=None, tensor_device=None, comm=None, transport: str = "nccl"):
+                 context_factory=None, tensor_device=None, comm=None, transport: str = "nccl",
+                 rebalance_every: int = 0, cuts: list | None = None):
         import torch
 
         if world.particle_sources:
@@ -74,12 +91,14 @@ class StripDomain:
         c = world.coefficients
         self.diameter = 2 * c["particle_radius"]
         rows = rows_of(pos, self.diameter)
-        self.cuts = partition_rows(rows, world_size, halo_rows)
+        self.cuts = list(cuts) if cuts is not None else partition_rows(rows, world_size, halo_rows)
+        assert len(self.cuts) == world_size + 1
         self.row_lo, self.row_hi = self.cuts[rank], self.cuts[rank + 1]
         mine = np.nonzero((rows >= self.row_lo) & (rows < self.row_hi))[0]
         per_row = max(int(np.bincount(rows - rows.min()).max()), 1)
         self.wire_capacity = int(wire_capacity or max(4 * (halo_rows + 2) * per_row, 1024))
-        capacity = int(len(mine) * slack) + 2 * self.wire_capacity + 1024
+        # room for this rank's share after re-balancing as well as for an unbalanced start
+        capacity = int(max(len(mine), -(-len(rows) // world_size)) * slack) + 2 * self.wire_capacity + 1024
         self.wire_capacity = min(self.wire_capacity, capacity)
         factory = context_factory or _lib.Context
         prec = {"f64": _lib.PRECISION_F64, "mixed": _lib.PRECISION_MIXED}[precision]
@@ -100,6 +119,15 @@ class StripDomain:
         self.ctx.set_state_uids(pos[mine], vel[mine], mine.astype(np.uint32))
         self.ctx.dist_configure(rank, world_size, self.row_lo, self.row_hi, halo_rows, self.wire_capacity)
         self.tick = 0
+        # re-balancing: every `rebalance_every` ticks the per-row histogram is summed over the ranks (the scheme's
+        # only collective) and the cuts then SLIDE towards the new equal-count positions by at most halo - 2 rows per
+        # tick, so the rows a cut hands over travel as ordinary migrants
+        self.rebalance_every = int(rebalance_every)
+        self.target_cuts = list(self.cuts)
+        self.max_cut_shift = max(halo_rows - 2, 1)
+        self._row0 = int(np.floor(-2 * c["particle_radius"] / self.diameter)) - 1
+        self._nrows = int(np.floor((1 + 2 * c["particle_radius"]) / self.diameter)) + 2 - self._row0
+        self._tensor_device = tensor_device
 
         nbytes = _lib.wire_bytes(self.wire_capacity) if context_factory is None else 16 + 40 * self.wire_capacity
         dev = tensor_device if tensor_device is not None else torch.device("cuda", device)
@@ -182,9 +210,38 @@ class StripDomain:
         for req in d.batch_isend_irecv(ops):
             req.wait()  # NCCL: the launch stream waits, the host does not
 
+    # ---- re-balancing -------------------------------------------------------------------------------------------
+    def rebalance(self) -> None:
+        """Collective (every rank, same tick): new equal-count target cuts from the global row histogram."""
+        import torch
+        import torch.distributed as dist
+        hist = self.ctx.dist_row_histogram(self._row0, self._nrows).astype(np.int64)
+        dev = self._tensor_device if self._tensor_device is not None else torch.device("cuda", self.ctx.device)
+        t = torch.from_numpy(hist).to(dev)
+        dist.all_reduce(t)
+        self.target_cuts = cuts_from_histogram(t.cpu().numpy(), self._row0, self.world_size, self.halo_rows)
+
+    def _slide_cuts(self) -> None:
+        """Every rank holds the whole cut list and moves it identically; no communication."""
+        new = list(self.cuts)
+        for k in range(1, self.world_size):
+            delta = self.target_cuts[k] - new[k]
+            new[k] += max(-self.max_cut_shift, min(self.max_cut_shift, delta))
+        for k in range(1, self.world_size):  # never squeeze an interior strip below two halos
+            if k >= 2 and new[k] - new[k - 1] < 2 * self.halo_rows:
+                new[k] = new[k - 1] + 2 * self.halo_rows
+        if new != self.cuts:
+            self.cuts = new
+            self.row_lo, self.row_hi = new[self.rank], new[self.rank + 1]
+            self.ctx.dist_set_rows(self.row_lo, self.row_hi)
+
     def physics_tick(self) -> None:
         self.ctx.set_tick(self.tick)
         if self.world_size > 1:
+            if self.rebalance_every and self.tick and self.tick % self.rebalance_every == 0:
+                self.rebalance()
+            if self.cuts != self.target_cuts:
+                self._slide_cuts()
             self.ctx.dist_pack(self.send_lo, self.send_hi)
             if self._symm is not None:
                 self._exchange_p2p()

@@ -31,12 +31,23 @@ def main():
     torch.cuda.set_stream(stream)
     ok = True
     transport = os.environ.get("SC_TRANSPORT", "nccl")
-    for maker, n, ticks, precision in ((dam_break, 200_000, 12, "f64"), (box_fill, 300_000, 8, "f64"),
-                                       (dam_break, 200_000, 12, "mixed")):
+    for maker, n, ticks, precision, rebalance in ((dam_break, 200_000, 12, "f64", 0), (box_fill, 300_000, 8, "f64", 0),
+                                                  (dam_break, 200_000, 12, "mixed", 0),
+                                                  (dam_break, 200_000, 16, "f64", 3)):
         world_cfg, pos, vel = maker(n)
-        vel = vel + np.random.RandomState(3).randn(*vel.shape) * (2.0 * world_cfg.coefficients["particle_radius"] / world_cfg.coefficients["dt"]) * 0.3
+        cuts = None
+        if rebalance:  # start from the equal-count cuts of ANOTHER scene (the column 0.1 higher): unbalanced here
+            from sand_crate_b200.strips import partition_rows, rows_of
+            shifted = pos.copy()
+            shifted[:, 1] -= 0.1
+            cuts = partition_rows(rows_of(shifted, 2 * world_cfg.coefficients["particle_radius"]), world)
+        # fast particles (0.3 d per tick): rows change hands every tick
+        vel = vel + np.random.RandomState(3).randn(*vel.shape) * (
+            2.0 * world_cfg.coefficients["particle_radius"] / world_cfg.coefficients["dt"]) * 0.3
         dom = StripDomain(world_cfg, pos, vel, rank=rank, world_size=world, precision=precision, noise="counter",
-                          noise_seed=5, device=local, stream=stream.cuda_stream, transport=transport)
+                          noise_seed=5, device=local, stream=stream.cuda_stream, transport=transport,
+                          rebalance_every=rebalance, cuts=cuts)
+        cuts0 = list(dom.cuts)
         own0 = set(dom.owned()[0].tolist())
         dom.step(ticks)
         st = dom.status()
@@ -53,7 +64,8 @@ def main():
             flags = any(s["overflow"] or s["too_far"] for _, s in moved_all)
             print(f"[mgpu] transport={transport} {maker.__name__} n={n} ticks={ticks} {precision} ranks={world}: "
                   f"bit-identical to single GPU = {same}; migrated = {[m for m, _ in moved_all]}; "
-                  f"local = {[s['n_local'] for _, s in moved_all]}; flags = {flags}", flush=True)
+                  f"local = {[s['n_local'] for _, s in moved_all]}; flags = {flags}; "
+                  f"rebalance_every = {rebalance}, cuts moved = {dom.cuts != cuts0}", flush=True)
             ok = ok and same and not flags and sum(m for m, _ in moved_all) > 0
             single.close()
         dom.close()

@@ -80,7 +80,14 @@ class OracleContext:
         self.uid = self.uid[~mask]
         self.pos, self.vel = pos, vel
 
+    def _sort_by_identity(self):
+        """The oracle breaks exact x ties by array index (= uid order in a single domain, like np.lexsort's
+        stability in the reference); a strip's local arrays are in arrival order, so restore uid order first."""
+        order = np.argsort(self.uid & np.uint32(0x7FFFFFFF), kind="stable")
+        self.pos, self.vel, self.uid = self.pos[order], self.vel[order], self.uid[order]
+
     def step_begin(self):
+        self._sort_by_identity()
         self._remove()
         seg, bl, bk = self.walls
         probe = O.step(self._coeffs(), self.pos, self.vel, seg, bl, bk, noise_mode=0)
@@ -164,6 +171,15 @@ class OracleContext:
             self.uid = np.concatenate((self.uid, np.where(r["kind"] == 1, r["uid"] | self.GHOST, r["uid"]))).astype(np.uint32)
         assert len(self.pos) <= self.capacity, "particle capacity overflow"
         self.prs = np.zeros(len(self.pos))
+
+    def dist_row_histogram(self, row0, nrows):
+        own = (self.uid & self.GHOST) == 0
+        d = 2 * self.params["particle_radius"]
+        rows = np.clip(np.floor(self.pos[own, 1] / d).astype(np.int64) - row0, 0, nrows - 1)
+        return np.bincount(rows, minlength=nrows).astype(np.uint64)
+
+    def dist_set_rows(self, row_lo, row_hi):
+        self.dist["lo"], self.dist["hi"] = row_lo, row_hi
 
     def dist_get_owned(self):
         own = (self.uid & self.GHOST) == 0

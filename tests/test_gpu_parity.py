@@ -334,7 +334,7 @@ def test_strips_two_gpus_bit_identical_to_single_gpu():
            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert res.stdout.count("bit-identical to single GPU = True") == 3, res.stdout
+    assert res.stdout.count("bit-identical to single GPU = True") == 4, res.stdout
 
 
 def test_force_monitor_on_gpu_matches_reference():

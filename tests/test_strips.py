@@ -47,14 +47,19 @@ def _coeff_vec(c):
                      c["target_pressure"], c["gravity"][0], c["gravity"][1]], dtype=np.float64)
 
 
-def _worker(rank, world_size, port, scene, n, ticks, out_dir):
+def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
-        world, pos, vel = (dam_break if scene == "dam_break" else box_fill)(n)
+        world, pos, vel = (box_fill if scene == "box_fill" else dam_break)(n)
+        if scene == "dam_break_shifted":   # start from a partition that is wrong for the scene: cuts must move
+            pos = pos.copy()
+            pos[:, 1] -= 0.1
         vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0  # fast particles: migration every tick
         dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision="f64", noise="counter",
-                          noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"))
+                          noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"),
+                          rebalance_every=rebalance_every)
+        cuts0 = list(dom.cuts)
         migrated = 0
         for _ in range(ticks):
             before = set(dom.ctx.dist_get_owned()[2].tolist())
@@ -65,7 +70,8 @@ def _worker(rank, world_size, port, scene, n, ticks, out_dir):
         if rank == 0:
             np.savez(os.path.join(out_dir, "out.npz"), uid=uid, pos=p, vel=v)
         stats = [None] * world_size
-        dist.all_gather_object(stats, (migrated, st["too_far"], st["n_local"]))
+        dist.all_gather_object(stats, (migrated, st["too_far"], st["n_local"], int(dom.cuts != cuts0),
+                                       len(dom.ctx.dist_get_owned()[2])))
         if rank == 0:
             np.save(os.path.join(out_dir, "stats.npy"), np.array(stats, dtype=np.int64))
     finally:
@@ -94,3 +100,31 @@ def test_strip_protocol_matches_single_domain(tmp_path, world_size, scene):
     assert np.array_equal(got["pos"], pos) and np.array_equal(got["vel"], vel)
     assert stats[:, 0].sum() > 0, "the test scene must exercise migration"
     assert not stats[:, 1].any(), "no particle may cross a whole halo in one tick"
+
+
+def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
+    """Re-balancing: the dam-break column collapses, rows change population, the cuts slide (<= halo - 2 rows per
+    tick) towards equal counts - and the result is still bit-identical to the single-domain run."""
+    n, ticks, world_size = 6000, 14, 3
+    mp.spawn(_worker, args=(world_size, _free_port(), "dam_break_shifted", n, ticks, str(tmp_path), 2),
+             nprocs=world_size, join=True)
+    got = np.load(tmp_path / "out.npz")
+    stats = np.load(tmp_path / "stats.npy")
+    world, pos, vel = dam_break(n)
+    pos = pos.copy()
+    pos[:, 1] -= 0.1
+    vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = _coeff_vec(world.coefficients)
+    uid = np.arange(n, dtype=np.uint32)
+    for tick in range(ticks):
+        pos, vel, mask = O.remove_particles(pos, vel, world.coefficients["particle_radius"])
+        uid = uid[~mask]
+        out = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(11, tick), uid=uid,
+                     want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+    assert np.array_equal(got["uid"], uid) and np.array_equal(got["pos"], pos) and np.array_equal(got["vel"], vel)
+    assert stats[:, 3].all(), "the cuts must have moved"
+    assert not stats[:, 1].any()
+    owned = stats[:, 4]
+    assert owned.max() - owned.min() < 0.25 * n / world_size, owned
