@@ -31,14 +31,14 @@ SURVEY_BYTES = {"prepass_wall_key": 20, "place": 14, "rank_gather": 56, "density
 
 
 # What THIS design moves per particle per launch: the same accounting plus the records K4 hands
-# to K5 (12 bytes per directed pair, K = measured mean pairs per particle) and the packed (p, s) record.
+# to K5 (8 bytes per directed pair, K = measured mean pairs per particle) and the packed (p, s) record.
 def algo_bytes(K):
     return {
         "prepass_wall_key": 16 + 4 + 4,                       # R pos; W key, slot
         "place": 4 + 4 + 4,                                   # R key, slot; W index
         "rank_gather": (4 + 4 + 16 + 8 + 4) + (16 + 8 + 8 + 4 + 4),   # R idx, key, pos, vel, uid; W pos, rel, vel, uid, key
-        "density": (8 + 4 + 4) + (16 + 4 + 1 + 12 * K),       # R rel, key, uid; W (p, s), pair offset/count, pair records
-        "force_integrate": (16 + 8 + 16 + 4 + 1 + 12 * K) + (16 + 8),  # R pos, vel, (p, s), offset/count, records; W pos, vel
+        "density": (8 + 4 + 4) + (16 + 4 + 1 + 8 * K),        # R rel, key, uid; W (p, s), pair offset/count, pair records
+        "force_integrate": (16 + 8 + 16 + 4 + 1 + 8 * K) + (16 + 8),   # R pos, vel, (p, s), offset/count, records; W pos, vel
     }
 
 

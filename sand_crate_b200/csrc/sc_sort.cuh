@@ -111,10 +111,9 @@ __device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32
     }
 }
 
-// Single-pass exclusive scan (decoupled look-back): one launch, 8 bytes of traffic per item.  Tiles take their index
-// from a ticket counter, so a tile's predecessors are always resident or done and the look-back cannot deadlock.
-// Tile descriptor = (status << 32) | value, written / read as one 64-bit word: status 1 = tile aggregate,
-// 2 = inclusive prefix.  `desc` (one word per tile) and `ticket` must be zero at launch.
+// Single-pass exclusive scan: one launch, 8 bytes of traffic per item.  Tiles take their index from a ticket counter,
+// so a tile's predecessors are always resident or done and waiting on them cannot deadlock.
+// Tile descriptor = (status << 32) | value, written / read as one 64-bit word: status 1 = tile aggregate published.  `desc` (one word per tile) and `ticket` must be zero at launch.
 __device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -140,31 +139,19 @@ k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__rest
     for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
     uint32_t total;
     const uint32_t before = block_exclusive_scan_n<SC_SCAN_THREADS>(v, total);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        if (lane == 0) st_desc(desc + tile, ((tile == 0 ? 2ull : 1ull) << 32) | total);
-        uint32_t exclusive = 0;
-        int look = (int)tile - 1;
-        while (look >= 0) {  // warp-wide window over the 32 nearest predecessors
-            const int idx = look - lane;
-            unsigned long long d;
-            do {
-                d = idx >= 0 ? ld_desc(desc + idx) : (2ull << 32);
-            } while (__any_sync(0xffffffffu, (d >> 32) == 0ull));
-            const unsigned has_prefix = __ballot_sync(0xffffffffu, (d >> 32) == 2ull);
-            const int first = has_prefix ? __ffs((int)has_prefix) - 1 : 31;  // nearest tile with a full prefix
-            uint32_t val = lane <= first ? (uint32_t)d : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-            exclusive += val;
-            if (has_prefix) break;
-            look -= 32;
-        }
-        if (lane == 0) {
-            if (tile != 0) st_desc(desc + tile, (2ull << 32) | (unsigned long long)(exclusive + total));
-            s_prefix = exclusive;
-        }
+    // publish this tile's aggregate, then read ALL predecessors' aggregates in parallel (one L2 round trip instead
+    // of a serial chain of look-back windows: with every tile starting at once, tile k would otherwise walk k / 32
+    // windows).  Lower tickets are always resident or finished, so the spin cannot deadlock.
+    if (threadIdx.x == 0) st_desc(desc + tile, (1ull << 32) | total);
+    uint32_t part = 0;
+    for (uint32_t t = threadIdx.x; t < tile; t += SC_SCAN_THREADS) {
+        unsigned long long d;
+        do { d = ld_desc(desc + t); } while ((d >> 32) == 0ull);
+        part += (uint32_t)d;
     }
+    uint32_t prefix;
+    block_exclusive_scan_n<SC_SCAN_THREADS>(part, prefix);
+    if (threadIdx.x == 0) s_prefix = prefix;
     __syncthreads();
     uint32_t run = s_prefix + before;
 #pragma unroll
