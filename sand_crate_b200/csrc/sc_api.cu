@@ -963,6 +963,33 @@ extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int6
     return 0;
 }
 
+// ---- developer aid (not part of the ABI in include/sandcrate.h): re-run one pair kernel of the last tick `reps` times
+// and return the mean milliseconds.  K4 and K5 only read the sorted set, so re-running them is harmless.
+extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
+    if (!ctx || !ctx->srt_valid) return -1.0;
+    cudaSetDevice(ctx->device);
+    DevParams dp = ctx->dp;
+    dp.noise_mode = ctx->noise_mode;
+    dp.tick_key = tick_key(ctx->seed, ctx->tick - 1);
+    const int64_t n = ctx->n_host;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float total = 0;
+    for (int r = 0; r < reps; ++r) {
+        if (which == 4) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
+        cudaEventRecord(e0, ctx->stream);
+        if (which == 4) launch_density<float>(ctx, ctx->grid, dp, nullptr, n);
+        else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return total / reps;
+}
+
 // ---- ForceMonitor (utils/force_monitor.py) ------------------------------------------------------------------------
 extern "C" int sc_set_monitor(sc_ctx *ctx, int on) {
     if (!ctx) return fail(ctx, "sc_set_monitor: NULL ctx");

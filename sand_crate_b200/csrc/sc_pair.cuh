@@ -27,6 +27,7 @@ template <> struct __align__(32) PS<double> { double p, sx, sy, pad_; };
 // word k * SC_BLOCK + t).  An entry is the neighbor's sorted index in the low 28 bits and the relative cell
 // (dr + 1) * 4 + (dc + 1) in the high 4.
 #define SC_IDX_MASK 0x0FFFFFFFu
+#define SC_K5_BATCH 2  // pairs whose loads K5 issues back to back (the pair loop is latency bound)
 struct NbrList {
     uint32_t *col;
     __device__ __forceinline__ uint32_t get(int k) const { return col[k * SC_BLOCK]; }
@@ -337,10 +338,8 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
             mpx = cx; mpy = cy;
         }
     };
-    const double2 ps = pos[s];
     const PS<Real> me = ps_in[s];
     const Real p_i = me.p;
-    const R2 v0 = vel[s];
     const uint32_t off = pair_off[s];
     const int K = pair_cnt[s];
     const Real smooth = (Real)P.smooth, two_target = (Real)(2 * P.target);
@@ -349,22 +348,22 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
     Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
     // batches of 4 pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
     // latency bound (two dependent L2 round trips per pair), so the loads of a batch are issued back to back
-    for (int k0 = 0; k0 < K; k0 += 4) {
-        uint32_t jj[4];
-        R2 nn[4];
-        PS<Real> pp[4];
-        R2 vv[4];
+    for (int k0 = 0; k0 < K; k0 += SC_K5_BATCH) {
+        uint32_t jj[SC_K5_BATCH];
+        R2 nn[SC_K5_BATCH];
+        PS<Real> pp[SC_K5_BATCH];
+        R2 vv[SC_K5_BATCH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < SC_K5_BATCH; ++u)
             if (k0 + u < K) PairIO<Real>::load(pair_j, pair_n, (size_t)off + k0 + u, jj[u], nn[u].x, nn[u].y);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < SC_K5_BATCH; ++u)
             if (k0 + u < K) {
                 pp[u] = ps_in[jj[u]];
                 if constexpr (sizeof(Real) == 4) vv[u] = vel[jj[u]];
             }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < SC_K5_BATCH; ++u)
             if (k0 + u < K) {
                 const R2 nv = nn[u];
                 const PS<Real> nb = pp[u];
@@ -420,6 +419,10 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         }
     }
 
+    // own position / velocity are only needed from here on: loading them late keeps the pair loop's register
+    // footprint (and with it the occupancy that hides the gather latency) small
+    const double2 ps = pos[s];
+    const R2 v0 = vel[s];
     const Real dt = (Real)P.dt;
     Real vx = v0.x, vy = v0.y;
     if constexpr (kMonitor) { mpx = (double)vx; mpy = (double)vy; }
