@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="strip exchange: NCCL send/recv or "
                     "direct NVLink stores into the neighbor's symmetric-memory buffer")
+    ap.add_argument("--rebalance-every", type=int, default=0, help="strips: re-cut the partition every N ticks")
     ap.add_argument("--mgpu-particles", type=int, default=2_000_000, help="particles per GPU when --gpus > 1")
     ap.add_argument("--cpu-particles", type=int, default=200_000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
@@ -255,7 +256,8 @@ def main():
         n_total = per_gpu * world_size
         world, pos, vel = SCENES[scene](n_total)
         dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
-                          device=local_rank, stream=stream, transport=a.transport)
+                          device=local_rank, stream=stream, transport=a.transport,
+                          rebalance_every=a.rebalance_every)
         ctx = dom.ctx
         step_fn = dom.physics_tick
         n = n_total // world_size
@@ -381,7 +383,7 @@ def main():
                        "local_particles_rank0": n_live,
                        "parallelism": "single GPU" if world_size == 1 else
                        f"{world_size} horizontal strips of cell rows, NCCL send/recv halo + migration with rank+-1 "
-                       f"every tick (halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, transport {dom.transport})",
+                       f"every tick (halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, transport {dom.transport}, re-cut every {dom.rebalance_every or 'never'})",
                        "dist_status_rank0": dist_status,
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
