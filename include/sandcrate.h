@@ -53,7 +53,7 @@ typedef struct sc_params {
 
 /* source of the per-directed-pair collider noise (crate.py:168-170) */
 #define SC_NOISE_NONE 0    /* term skipped; exact when collider_noise_level == 0 */
-#define SC_NOISE_COUNTER 1 /* counter-based: mix64((uid_i << 32 | uid_j) ^ tick_key(seed, tick)) */
+#define SC_NOISE_COUNTER 1 /* counter-based: lowbias32(uid_i * C1 ^ uid_j * C2 ^ fold32(tick_key(seed, tick))), 2 x 16 bits */
 #define SC_NOISE_HOST 2    /* the caller supplies the reference's own np.random.rand stream per tick */
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

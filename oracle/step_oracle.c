@@ -51,10 +51,10 @@ static inline uint32_t oc_lowbias32(uint32_t x) {
 }
 void oc_pair_noise(uint64_t tick_key, uint32_t uid_i, uint32_t uid_j, double *ux, double *uy) {
     const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
-    const uint32_t hx = oc_lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (uint32_t)tick_key);
-    const uint32_t hy = oc_lowbias32(hx ^ (uint32_t)(tick_key >> 32));
-    *ux = (double)hx * (1.0 / 4294967296.0);
-    *uy = (double)hy * (1.0 / 4294967296.0);
+    const uint32_t h = oc_lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^
+                                    ((uint32_t)tick_key ^ (uint32_t)(tick_key >> 32)));
+    *ux = (double)(h >> 16) * (1.0 / 65536.0);   /* high half: x uniform, low half: y uniform */
+    *uy = (double)(h & 0xFFFFu) * (1.0 / 65536.0);
 }
 
 /* ------------------------------------------------------------------------------------------------------ */

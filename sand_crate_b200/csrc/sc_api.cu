@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,6 +41,8 @@ struct sc_ctx {
     // particle state: *_cur = current state (order left by the previous tick), *_srt = this tick's sorted gather
     double2 *pos_cur = nullptr, *pos_srt = nullptr;
     float2 *rel_srt = nullptr;        // cell-relative fp32 positions of the sorted set
+    float4 *rec_srt = nullptr;        // mixed mode: (rel, cell column, uid) search records of the tiled pair kernels
+    BlockDesc *blk_desc = nullptr;    // mixed mode: per block of SC_BLOCK sorted particles, its three windows
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
     uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
@@ -62,6 +65,8 @@ struct sc_ctx {
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
     bool lists_valid = false, rank_valid = false;
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
+    int pair_mode = 1;  // mixed mode with device noise: 0 = untiled K4/K5, 1 = tiled K4 + untiled K5, 2 = both tiled
+                        // (developer switch: SC_PAIR_MODE)
     bool monitor_on = false;  // ForceMonitor mode: K5 also sums |dv| per force stage
     double *monitor = nullptr; // 6 sums + particle count of the last tick
     bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
@@ -110,6 +115,7 @@ static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + SC_BLOCK -
 struct ProfScope {
     sc_ctx *c; int slot; cudaEvent_t e0 = nullptr, e1 = nullptr;
     ProfScope(sc_ctx *c_, int slot_) : c(c_), slot(slot_) {
+        if (slot < 0) return;  // the caller has opened a scope for this launch
         c->launches++;
         if (!c->profiling) return;
         auto get = [&]() {
@@ -121,7 +127,7 @@ struct ProfScope {
         cudaEventRecord(e0, c->stream);
     }
     ~ProfScope() {
-        if (!c->profiling) return;
+        if (slot < 0 || !c->profiling) return;
         cudaEventRecord(e1, c->stream);
         c->pending.push_back({slot, e0, e1});
     }
@@ -241,6 +247,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     sc_ctx *c = new sc_ctx();
     ctx = c;
     c->device = device; c->precision = precision; c->cap = capacity;
+    { const char *e_ = getenv("SC_PAIR_MODE"); if (e_ && e_[0] >= '0' && e_[0] <= '2') c->pair_mode = e_[0] - '0'; }
     if (stream) c->stream = (cudaStream_t)stream;
     else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
     const size_t n = (size_t)capacity, rs = real_size(c);
@@ -251,6 +258,10 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
     rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
     rc |= dev_alloc(c, &c->rel_srt, n);
+    if (precision == SC_PRECISION_MIXED) {
+        rc |= dev_alloc(c, &c->rec_srt, n);
+        rc |= dev_alloc(c, &c->blk_desc, (n + SC_BLOCK - 1) / SC_BLOCK + 1);
+    }
     rc |= dev_alloc(c, (char **)&c->ps, n * 4 * rs);
     rc |= dev_alloc(c, &c->pair_j, n * SC_MAX_NEIGHBORS);
     rc |= dev_alloc(c, (char **)&c->pair_n, n * SC_MAX_NEIGHBORS * 2 * rs);
@@ -273,7 +284,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy, c->monitor};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -563,12 +574,12 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
             CK(launch_pdl(k_rank_gather<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
                 ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt));
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, (float4 *)nullptr, (BlockDesc *)nullptr));
         else
             CK(launch_pdl(k_rank_gather<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
                 ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt));
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->rec_srt, ctx->blk_desc));
     }
     CK(cudaGetLastError());
     ctx->srt_valid = true;
@@ -619,10 +630,10 @@ static int launch_density(sc_ctx *ctx, const Grid &g, const DevParams &dp, const
 }
 
 template <typename Real>
-static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n) {
+static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n, bool scoped = true) {
     typedef typename Vec2<Real>::type R2;
-    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
-    ProfScope ps(ctx, SLOT_FORCE);
+    if (scoped && ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    ProfScope ps(ctx, scoped ? SLOT_FORCE : -1);
     auto go = [&](auto kernel) {
         return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
                           (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
@@ -631,6 +642,40 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
     };
     CK(ctx->monitor_on ? go(k_force<Real, true>) : go(k_force<Real, false>));
     return 0;
+}
+
+// mixed precision with device-side noise: the pair kernels that stage the block's neighborhood in shared memory.
+// pair_mode 1: tiled K4 + untiled K5 (records carry sorted indices); 2: both tiled (records carry local indices)
+static int launch_density_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt, g, dp, ctx->cell_start,
+                          ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt, (uint2 *)ctx->pair_n,
+                          ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
+    };
+    const bool counter = dp.noise_mode == SC_NOISE_COUNTER;
+    if (ctx->pair_mode == 1) CK(counter ? go(k_density_tile<SC_NOISE_COUNTER, true>) : go(k_density_tile<SC_NOISE_NONE, true>));
+    else CK(counter ? go(k_density_tile<SC_NOISE_COUNTER, false>) : go(k_density_tile<SC_NOISE_NONE, false>));
+    return 0;
+}
+static int launch_force_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
+    if (ctx->pair_mode == 1) return launch_force<float>(ctx, dp, ctx->cell_start + g.ncells, n, false);
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, g, dp, ctx->walls, ctx->cell_start,
+                          ctx->blk_desc, ctx->pos_srt, (const float2 *)ctx->vel_srt, (const uint2 *)ctx->pair_n,
+                          ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps, ctx->wall_bits_srt,
+                          ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->monitor);
+    };
+    CK(ctx->monitor_on ? go(k_force_tile<true>) : go(k_force_tile<false>));
+    return 0;
+}
+static int launch_tiled(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
+    {
+        ProfScope ps(ctx, SLOT_DENSITY);
+        CKR(launch_density_tile(ctx, g, dp, n));
+    }
+    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    ProfScope ps(ctx, SLOT_FORCE);
+    return launch_force_tile(ctx, g, dp, n);
 }
 
 static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
@@ -648,12 +693,14 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
                 CKR(launch_density<double>(ctx, g, dp, noise_off, n));
             }
             CKR(launch_force<double>(ctx, dp, n_ptr, n));
-        } else {
+        } else if (dp.noise_mode == SC_NOISE_HOST || (ctx->pair_mode == 0)) {
             {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 CKR(launch_density<float>(ctx, g, dp, noise_off, n));
             }
             CKR(launch_force<float>(ctx, dp, n_ptr, n));
+        } else {
+            CKR(launch_tiled(ctx, g, dp, n));
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
@@ -976,10 +1023,22 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float total = 0;
     for (int r = 0; r < reps; ++r) {
-        if (which == 4) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
+        if (which == 4 || which == 24) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
         cudaEventRecord(e0, ctx->stream);
-        if (which == 4) launch_density<float>(ctx, ctx->grid, dp, nullptr, n);
-        else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n);
+        const bool tiled = ctx->pair_mode != 0 && dp.noise_mode != SC_NOISE_HOST;
+        if (which == 25) {
+            typedef float2 R2;
+            launch_pdl(k_force<float, false, true>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
+                       (const uint32_t *)(ctx->cell_start + ctx->grid.ncells), dp, ctx->walls, ctx->pos_srt,
+                       (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
+                       (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
+                       (R2 *)ctx->vel_cur, ctx->monitor);
+        } else if (which == 24) {
+            launch_pdl(k_density_tile<SC_NOISE_COUNTER, false, 2>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt,
+                       ctx->grid, dp, ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt,
+                       (uint2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
+        } else if (which == 4) { if (tiled) launch_density_tile(ctx, ctx->grid, dp, n); else launch_density<float>(ctx, ctx->grid, dp, nullptr, n); }
+        else { if (tiled) launch_force_tile(ctx, ctx->grid, dp, n); else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n); }
         cudaEventRecord(e1, ctx->stream);
         cudaEventSynchronize(e1);
         float ms = 0;

@@ -77,9 +77,10 @@ struct Counters {
 
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
 // Host side: tick_key = splitmix64 finalizer of (seed, tick).  Device side, per DIRECTED pair (i <- j), 32-bit
-// arithmetic only: the two uids are spread with distinct odd multipliers, keyed with the low word of tick_key and
-// mixed with the lowbias32 finalizer (2 multiplies, 3 xor-shifts) for the x uniform; the y uniform is a second
-// lowbias32 round keyed with the high word.  Bit 31 of a uid marks a ghost copy in the strip decomposition
+// arithmetic only: the two uids are spread with distinct odd multipliers, keyed with the two halves of tick_key
+// folded together, and mixed with the lowbias32 finalizer (2 multiplies, 3 xor-shifts).  The high 16 bits of the
+// result are the x uniform, the low 16 bits the y uniform (k / 65536: exact in fp32 and fp64 alike; the noise
+// amplitude is 0.1 d, so the grain is 1.5e-6 d).  Bit 31 of a uid marks a ghost copy in the strip decomposition
 // (sc_dist.cuh) and is not part of the identity.
 __host__ __device__ inline uint64_t mix64(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
@@ -96,10 +97,14 @@ __host__ __device__ inline uint32_t lowbias32(uint32_t x) {
     x ^= x >> 16;
     return x;
 }
-__host__ __device__ inline void pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j, uint32_t &hx, uint32_t &hy) {
+__host__ __device__ inline uint32_t pair_noise_bits(uint64_t tkey, uint32_t uid_i, uint32_t uid_j) {
     const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
-    hx = lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ (uint32_t)tkey);
-    hy = lowbias32(hx ^ (uint32_t)(tkey >> 32));
+    return lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ ((uint32_t)tkey ^ (uint32_t)(tkey >> 32)));
+}
+// the two uniforms as fp32 in [1, 2) (k / 65536 + 1): bits dropped straight into the mantissa, no int-to-float convert
+__device__ __forceinline__ void pair_noise_f32_1to2(uint32_t h, float &fx, float &fy) {
+    fx = __uint_as_float(0x3F800000u | ((h >> 9) & 0x007FFF80u));
+    fy = __uint_as_float(0x3F800000u | ((h << 7) & 0x007FFF80u));
 }
 
 // ---- geometry_utils.py:7-39 for one (point, segment) -----------------------------------------------------

@@ -114,10 +114,9 @@ __device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, do
             ux = host_noise[2 * (size_t)noise_index];
             uy = host_noise[2 * (size_t)noise_index + 1];
         } else {
-            uint32_t hx, hy;
-            pair_noise_bits(P.tick_key, uid_i, uid_j, hx, hy);
-            ux = (double)hx * (1.0 / 4294967296.0);
-            uy = (double)hy * (1.0 / 4294967296.0);
+            const uint32_t h = pair_noise_bits(P.tick_key, uid_i, uid_j);
+            ux = (double)(h >> 16) * (1.0 / 65536.0);
+            uy = (double)(h & 0xFFFFu) * (1.0 / 65536.0);
         }
         qx += (ux - 0.5) * P.d * P.level;
         qy += (uy - 0.5) * P.d * P.level;
@@ -146,11 +145,10 @@ __device__ __forceinline__ PairGeom<float> pair_geom_f32(const DevParams &P, flo
             ux = (float)host_noise[2 * (size_t)noise_index];
             uy = (float)host_noise[2 * (size_t)noise_index + 1];
         } else {
-            uint32_t hx, hy;
-            pair_noise_bits(P.tick_key, uid_i, uid_j, hx, hy);
-            // top 23 bits into the mantissa of [1, 2): no integer-to-float conversion on the hot path
-            ux = __uint_as_float(0x3F800000u | (hx >> 9)) - 1.0f;
-            uy = __uint_as_float(0x3F800000u | (hy >> 9)) - 1.0f;
+            float fx, fy;
+            pair_noise_f32_1to2(pair_noise_bits(P.tick_key, uid_i, uid_j), fx, fy);
+            ux = fx - 1.0f;
+            uy = fy - 1.0f;
         }
         const float amp = (float)(P.d * P.level);
         rx = fmaf(0.5f - ux, amp, rx);
@@ -311,24 +309,19 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
     ps_out[s] = o;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K5: all forces, wall bounce, continuous collision and integration for particle s
-// kMonitor: also accumulate, per force stage, the sum over particles of |dv| (the reference's ForceMonitor,
-// utils/force_monitor.py:23-33, wraps exactly these six stages: crate.py:110-124)
-template <typename Real, bool kMonitor>
-__global__ void __launch_bounds__(SC_BLOCK)
-k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
-        const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
-        const uint32_t *__restrict__ pair_j, const typename Vec2<Real>::type *__restrict__ pair_n,
-        const uint32_t *__restrict__ pair_off, const uint8_t *__restrict__ pair_cnt,
-        const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
-        const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
-        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out,
-        double *__restrict__ monitor) {
-    pdl_enter();
+// Everything of K5 that follows the pair loop, for particle s: wall contact rows of F5, F3-F6 velocity updates, wall
+// bounce, continuous collision, integration.  `visc(vx, vy, ax, ay)` supplies sum_j (v_j - v) (crate.py:319-323).
+template <typename Real, bool kMonitor, bool kNoRare = false, typename ViscFn>
+__device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx, Real ty, Real qx, Real qy,
+                                           const DevParams &P, const WallParams &W, const double2 *__restrict__ pos,
+                                           const typename Vec2<Real>::type *__restrict__ vel,
+                                           const uint32_t *__restrict__ wall_bits,
+                                           const uint32_t *__restrict__ wall_slot,
+                                           const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out,
+                                           typename Vec2<Real>::type *__restrict__ vel_out,
+                                           double *__restrict__ monitor, const uint32_t *__restrict__ n_ptr,
+                                           ViscFn visc) {
     typedef typename Vec2<Real>::type R2;
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= *n_ptr) return;
     double mon[6] = {0, 0, 0, 0, 0, 0};
     double mpx = 0, mpy = 0;  // velocity before the current stage
     auto stage = [&](int q, double cx, double cy) {
@@ -338,56 +331,12 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
             mpx = cx; mpy = cy;
         }
     };
-    const PS<Real> me = ps_in[s];
-    const Real p_i = me.p;
-    const uint32_t off = pair_off[s];
-    const int K = pair_cnt[s];
-    const Real smooth = (Real)P.smooth, two_target = (Real)(2 * P.target);
-    Real tx = 0, ty = 0;  // F3 sum
-    Real qx = 0, qy = 0;  // F5 sum
-    Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
-    // batches of 4 pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
-    // latency bound (two dependent L2 round trips per pair), so the loads of a batch are issued back to back
-    for (int k0 = 0; k0 < K; k0 += SC_K5_BATCH) {
-        uint32_t jj[SC_K5_BATCH];
-        R2 nn[SC_K5_BATCH];
-        PS<Real> pp[SC_K5_BATCH];
-        R2 vv[SC_K5_BATCH];
-#pragma unroll
-        for (int u = 0; u < SC_K5_BATCH; ++u)
-            if (k0 + u < K) PairIO<Real>::load(pair_j, pair_n, (size_t)off + k0 + u, jj[u], nn[u].x, nn[u].y);
-#pragma unroll
-        for (int u = 0; u < SC_K5_BATCH; ++u)
-            if (k0 + u < K) {
-                pp[u] = ps_in[jj[u]];
-                if constexpr (sizeof(Real) == 4) vv[u] = vel[jj[u]];
-            }
-#pragma unroll
-        for (int u = 0; u < SC_K5_BATCH; ++u)
-            if (k0 + u < K) {
-                const R2 nv = nn[u];
-                const PS<Real> nb = pp[u];
-                // F3 pass 2, crate.py:347-353
-                const Real ddx = me.sx - nb.sx, ddy = me.sy - nb.sy;
-                const Real align = (ddx * nv.x + ddy * nv.y) * smooth;
-                const Real fix = nb.p + p_i - two_target;
-                const Real cc = align + fix;
-                const Real ex = cc * nv.x, ey = cc * nv.y;
-                // F5, crate.py:301-306
-                const Real ps_ = p_i + nb.p;
-                const Real fx = nv.x * ps_, fy = nv.y * ps_;
-                if (k0 + u == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
-                else { tx += ex; ty += ey; qx += fx; qy += fy; }
-                if constexpr (sizeof(Real) == 4) { sum_vx += vv[u].x; sum_vy += vv[u].y; }
-            }
-    }
-
     // walls: contacts are recomputed from the position the particle had BEFORE apply_hard_wall_fix
     // (crate.py:216 runs before 202-211 and the vectors are never refreshed)
     int V = 0;
     double wnx = 0, wny = 0, wux = 0, wuy = 0;  // sequential sums for np.mean (crate.py:249-250)
     const bool touching = (wall_bits[s >> 5] >> (s & 31)) & 1u;
-    if (touching) {
+    if (!kNoRare && touching) {
         const double2 pre = wall_pre[wall_slot[s]];
         int nb[SC_MAX_BODIES];
         for (int b = 0; b < W.nbodies; ++b) nb[b] = 0;
@@ -437,16 +386,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
     stage(2, (double)vx, (double)vy);
     {                                                                    // F6, crate.py:319-323
         Real ax = 0, ay = 0;
-        if constexpr (sizeof(Real) == 8) {
-            for (int q = 0; q < K; ++q) {
-                const R2 vj = vel[PairIO<Real>::load_index(pair_j, pair_n, (size_t)off + q)];
-                const Real ex = vj.x - vx, ey = vj.y - vy;
-                if (q == 0) { ax = ex; ay = ey; } else { ax += ex; ay += ey; }
-            }
-        } else {
-            ax = sum_vx - (Real)K * vx;
-            ay = sum_vy - (Real)K * vy;
-        }
+        visc(vx, vy, ax, ay);
         const Real c = (Real)(P.dt * P.visc);
         vx += c * ax; vy += c * ay;
     }
@@ -473,7 +413,7 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
         const double mxlo = fmin(ps.x, bx), mxhi = fmax(ps.x, bx), mylo = fmin(ps.y, by), myhi = fmax(ps.y, by);
         // one test for the bulk of the liquid: the movement stays inside a rectangle no padded segment reaches
         const bool clear = mxlo > W.safe_ccd[0] && mxhi < W.safe_ccd[1] && mylo > W.safe_ccd[2] && myhi < W.safe_ccd[3];
-        if (!clear) {
+        if (!kNoRare && !clear) {
             const double bax = bx - ps.x, bay = by - ps.y;
             for (int q = 0; q < 2 * W.S; ++q) {
                 if (mxhi < W.pad_box[q][0] || mxlo > W.pad_box[q][1] || myhi < W.pad_box[q][2] || mylo > W.pad_box[q][3])
@@ -506,6 +446,86 @@ k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__
     po.x = ps.x + P.dt * (double)vo.x;
     po.y = ps.y + P.dt * (double)vo.y;
     pos_out[s] = po;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: all forces, wall bounce, continuous collision and integration for particle s
+// kMonitor: also accumulate, per force stage, the sum over particles of |dv| (the reference's ForceMonitor,
+// utils/force_monitor.py:23-33, wraps exactly these six stages: crate.py:110-124)
+#ifndef SC_K5_MINBLOCKS
+#define SC_K5_MINBLOCKS 1
+#endif
+template <typename Real, bool kMonitor, bool kNoRare = false>  // kNoRare: developer timing aid (wrong results)
+__global__ void __launch_bounds__(SC_BLOCK, SC_K5_MINBLOCKS)
+k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
+        const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
+        const uint32_t *__restrict__ pair_j, const typename Vec2<Real>::type *__restrict__ pair_n,
+        const uint32_t *__restrict__ pair_off, const uint8_t *__restrict__ pair_cnt,
+        const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
+        const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
+        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out,
+        double *__restrict__ monitor) {
+    pdl_enter();
+    typedef typename Vec2<Real>::type R2;
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= *n_ptr) return;
+    const PS<Real> me = ps_in[s];
+    const Real p_i = me.p;
+    const uint32_t off = pair_off[s];
+    const int K = pair_cnt[s];
+    const Real smooth = (Real)P.smooth, two_target = (Real)(2 * P.target);
+    Real tx = 0, ty = 0;  // F3 sum
+    Real qx = 0, qy = 0;  // F5 sum
+    Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
+    // batches of 4 pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
+    // latency bound (two dependent L2 round trips per pair), so the loads of a batch are issued back to back
+    for (int k0 = 0; k0 < K; k0 += SC_K5_BATCH) {
+        uint32_t jj[SC_K5_BATCH];
+        R2 nn[SC_K5_BATCH];
+        PS<Real> pp[SC_K5_BATCH];
+        R2 vv[SC_K5_BATCH];
+#pragma unroll
+        for (int u = 0; u < SC_K5_BATCH; ++u)
+            if (k0 + u < K) PairIO<Real>::load(pair_j, pair_n, (size_t)off + k0 + u, jj[u], nn[u].x, nn[u].y);
+#pragma unroll
+        for (int u = 0; u < SC_K5_BATCH; ++u)
+            if (k0 + u < K) {
+                pp[u] = ps_in[jj[u]];
+                if constexpr (sizeof(Real) == 4) vv[u] = vel[jj[u]];
+            }
+#pragma unroll
+        for (int u = 0; u < SC_K5_BATCH; ++u)
+            if (k0 + u < K) {
+                const R2 nv = nn[u];
+                const PS<Real> nb = pp[u];
+                // F3 pass 2, crate.py:347-353
+                const Real ddx = me.sx - nb.sx, ddy = me.sy - nb.sy;
+                const Real align = (ddx * nv.x + ddy * nv.y) * smooth;
+                const Real fix = nb.p + p_i - two_target;
+                const Real cc = align + fix;
+                const Real ex = cc * nv.x, ey = cc * nv.y;
+                // F5, crate.py:301-306
+                const Real ps_ = p_i + nb.p;
+                const Real fx = nv.x * ps_, fy = nv.y * ps_;
+                if (k0 + u == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
+                else { tx += ex; ty += ey; qx += fx; qy += fy; }
+                if constexpr (sizeof(Real) == 4) { sum_vx += vv[u].x; sum_vy += vv[u].y; }
+            }
+    }
+
+    force_tail<Real, kMonitor, kNoRare>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
+                               monitor, n_ptr, [&](Real vx, Real vy, Real &ax, Real &ay) {
+        if constexpr (sizeof(Real) == 8) {
+            for (int q = 0; q < K; ++q) {
+                const R2 vj = vel[PairIO<Real>::load_index(pair_j, pair_n, (size_t)off + q)];
+                const Real ex = vj.x - vx, ey = vj.y - vy;
+                if (q == 0) { ax = ex; ay = ey; } else { ax += ex; ay += ey; }
+            }
+        } else {
+            ax = sum_vx - (Real)K * vx;
+            ay = sum_vy - (Real)K * vy;
+        }
+    });
 }
 
 }  // namespace sc

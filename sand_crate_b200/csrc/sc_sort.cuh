@@ -4,6 +4,7 @@
 // are bit-identical to the reference's in BOTH precision modes.
 #pragma once
 #include "sc_pair.cuh"
+#include "sc_tile.cuh"
 
 namespace sc {
 
@@ -13,7 +14,10 @@ namespace sc {
 //   kStep = true : remove_particles (crate.py:149-159), calc_virtual_colliders + apply_hard_wall_fix
 //                  (crate.py:213-243, 202-211), then the cell key
 //   kStep = false: cell key only (standalone detect_particle_collisions)
-#define SC_PREPASS_ILP 2  // particles per thread: the kernel is a chain of two long-latency operations (position
+#ifndef SC_PREPASS_ILP
+#define SC_PREPASS_ILP 2
+#endif
+//                     ^ // particles per thread: the kernel is a chain of two long-latency operations (position
                           // load, histogram atomic), so independent chains are interleaved
 template <bool kStep>
 __global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it is rare
@@ -94,7 +98,10 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
 // exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply).
 // 16 items per thread as four 128-bit accesses: a warp request covers 2 KB contiguous.
 #define SC_SCAN_ITEMS 16
-#define SC_SCAN_THREADS 1024  // few, large tiles: the look-back of tile k walks k / 32 windows when all start together
+#ifndef SC_SCAN_THREADS
+#define SC_SCAN_THREADS 1024
+#endif
+//                      ^ // few, large tiles: the look-back of tile k walks k / 32 windows when all start together
 #define SC_SCAN_TILE (SC_SCAN_THREADS * SC_SCAN_ITEMS)
 
 __device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {
@@ -208,7 +215,7 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
               double2 *__restrict__ pos_s, float2 *__restrict__ rel_s,
               typename Vec2<Real>::type *__restrict__ vel_s, uint32_t *__restrict__ uid_s,
               uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
-              uint32_t *__restrict__ wall_slot_s) {
+              uint32_t *__restrict__ wall_slot_s, SearchRec *__restrict__ rec_s, BlockDesc *__restrict__ desc) {
     pdl_enter();
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,6 +242,17 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
         r.x = (float)(p.x - (double)((int)cc + g.col_min) * g.d);
         r.y = (float)(p.y - (double)((int)cr + g.row_min) * g.d);
         rel_s[f] = r;
+        // the tiled pair kernels read position, cell column and identity as one 16-byte record (sc_tile.cuh)
+        if (rec_s) rec_s[f] = make_float4(r.x, r.y, (float)cc, __uint_as_float(u));
+    }
+    if (desc) {  // the block of the tiled pair kernels this particle opens / closes: its three windows (sc_tile.cuh)
+        const uint32_t nc = (uint32_t)g.ncols;
+        if ((f & (SC_BLOCK - 1u)) == 0u)
+            reinterpret_cast<uint4 *>(desc + f / SC_BLOCK)[0] =
+                make_uint4(cell_start[c - 1u], cell_start[c + nc - 1u], cell_start[c - nc - 1u], c);
+        if ((f & (SC_BLOCK - 1u)) == SC_BLOCK - 1u || f == n - 1u)
+            reinterpret_cast<uint4 *>(desc + f / SC_BLOCK)[1] =
+                make_uint4(cell_start[c + 2u], cell_start[c + nc + 2u], cell_start[c - nc + 2u], c);
     }
     vel_s[f] = vel[i];
     uid_s[f] = u;

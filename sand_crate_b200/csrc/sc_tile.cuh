@@ -1,0 +1,373 @@
+// sc_tile.cuh - the production (mixed precision, device noise) pair kernels: K4 and K5 with the neighborhood of a
+// block staged in shared memory.
+//
+// A block owns SC_BLOCK consecutive particles of the sorted set.  Because the sort is cell-major (row, col, x), every
+// neighbor of those particles lies in one of three CONTIGUOUS windows of the sorted set - the block's own stretch of
+// its cell row(s) widened by one cell at each end, and the same stretch of cells one row below / one row above:
+//
+//     W0 = [cell_start[c_lo - 1],         cell_start[c_hi + 2])           same row(s)
+//     W1 = [cell_start[c_lo + ncols - 1], cell_start[c_hi + ncols + 2])   next row(s)
+//     W2 = [cell_start[c_lo - ncols - 1], cell_start[c_hi - ncols + 2])   previous row(s)
+//
+// (c_lo, c_hi = cells of the block's first / last particle).  The windows are copied into shared memory once with
+// coalesced 16-byte loads; the candidate loop (K4) and the neighbor gathers (K5) then read shared memory instead of
+// issuing one dependent global load per candidate / per pair.  A staged particle is addressed by its position in the
+// concatenation W0 | W1 | W2 ("local index"); K4 writes local indices into the pair records, and K5, which cuts the
+// sorted set into the same blocks, stages the same windows and resolves them without any translation.
+//
+// When the three windows do not fit the staging buffer (a block of spray that spans many sparse rows), the block
+// runs the same code with a pass-through accessor: local index = sorted index, reads go to global memory.  The
+// arithmetic is identical in both modes, so a particle's result does not depend on which mode its block ran in
+// (the strip decomposition relies on that: a ghost and its owner must compute the same bits).
+//
+// What the kernels compute is what sc_pair.cuh computes (same reference lines, same list order, same 20-trim, same
+// fp32-screen / fp64-replay acceptance); only the data movement differs.
+#pragma once
+#include "sc_pair.cuh"
+
+namespace sc {
+
+#define SC_TILE_CAP 1280    // staged particles per block (3 windows of ~SC_BLOCK + a few cells each)
+#define SC_TILE_CELLS 448   // staged cell boundaries per row (blocks that wrap around a row end read them from global)
+
+// search record of one sorted particle, written by k_rank_gather in mixed mode:
+//   x, y = cell-relative position (see collect_neighbors), z = (float)cell column, w = uid bits
+// The column travels as a float so that the x offset between two cells is one subtraction and one FMA:
+//   x_j - x_i = (rel_j.x - rel_i.x) + (col_j - col_i) * d     with col_j - col_i in {-1, 0, 1}, exact in fp32.
+typedef float4 SearchRec;
+
+// Per block of SC_BLOCK sorted particles, written by k_rank_gather (the threads that place the block's first and last
+// particle): the three windows and the block's first / last cell.  One 32-byte read replaces a chain of dependent
+// loads (particle count -> cell keys -> cell boundaries) at the head of K4 and K5.
+struct __align__(16) BlockDesc {
+    uint32_t base[3], c_lo;  // first sorted index of W0, W1, W2
+    uint32_t end[3], c_hi;   // one past the last
+};
+
+struct TileWindows {
+    uint32_t base[3];  // first sorted index of W0, W1, W2
+    uint32_t off[3];   // first local index of W0, W1, W2 (staged) / = base (pass-through)
+    uint32_t total;    // staged particles
+    uint32_t c_lo, ncw;  // first cell of the block, cells per row slice (c_lo - 1 .. c_hi + 2)
+    bool staged, cells_staged;
+};
+
+__device__ __forceinline__ TileWindows tile_windows(const BlockDesc *__restrict__ desc) {
+    const uint4 lo = reinterpret_cast<const uint4 *>(desc)[0], hi = reinterpret_cast<const uint4 *>(desc)[1];
+    TileWindows w;
+    w.base[0] = lo.x; w.base[1] = lo.y; w.base[2] = lo.z; w.c_lo = lo.w;
+    const uint32_t n0 = hi.x - lo.x, n1 = hi.y - lo.y, n2 = hi.z - lo.z;
+    w.total = n0 + n1 + n2;
+    w.ncw = hi.w - lo.w + 4u;
+    w.staged = w.total <= SC_TILE_CAP;
+    w.cells_staged = w.staged && w.ncw <= SC_TILE_CELLS;
+    if (w.staged) { w.off[0] = 0u; w.off[1] = n0; w.off[2] = n0 + n1; }
+    else { w.off[0] = w.base[0]; w.off[1] = w.base[1]; w.off[2] = w.base[2]; }
+    return w;
+}
+
+// sorted index of the staged particle at local index t (used only while staging)
+__device__ __forceinline__ uint32_t tile_source(const TileWindows &w, uint32_t t) {
+    return t < w.off[1] ? w.base[0] + t : (t < w.off[2] ? w.base[1] + (t - w.off[1]) : w.base[2] + (t - w.off[2]));
+}
+
+// accessors: shared memory by 32-bit shared address (keeps the address arithmetic to one instruction), or global
+template <typename T> struct SmemAcc {
+    uint32_t addr;
+    __device__ __forceinline__ T get(uint32_t L) const;
+};
+template <> __device__ __forceinline__ float4 SmemAcc<float4>::get(uint32_t L) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + L * 16u));
+    return v;
+}
+template <> __device__ __forceinline__ float2 SmemAcc<float2>::get(uint32_t L) const {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr + L * 8u));
+    return v;
+}
+template <typename T> struct GmemAcc {
+    const T *__restrict__ p;
+    __device__ __forceinline__ T get(uint32_t L) const { return p[L]; }
+};
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// per-thread neighbor list, one column per thread; 16-bit entries when the indices are local (11 bits + row code)
+template <typename E, int kShift> struct TileList {
+    E *col;
+    __device__ __forceinline__ void set(int k, uint32_t L, uint32_t code) { col[k * SC_BLOCK] = (E)(L | (code << kShift)); }
+    __device__ __forceinline__ void get(int k, uint32_t &L, uint32_t &code) const {
+        const uint32_t e = col[k * SC_BLOCK];
+        L = e & ((1u << kShift) - 1u); code = e >> kShift;
+    }
+};
+
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4 body for one particle.  s = sorted index; b[] = the six boundaries of its four candidate ranges as LOCAL
+// indices (m0, m3 | n0, n3 | p0, p3 of collect_neighbors, shifted into the staged windows).  List order = reference
+// list order.  kGlobalIdx: the pair records carry sorted indices (consumed by the untiled K5) instead of local ones.
+template <int kNoise, bool kGlobalIdx, class Acc, class List>
+__device__ __forceinline__ void density_particle(const Acc &A, List lst, const TileWindows &w, bool live, uint32_t s,
+                                                 const uint32_t (&b)[6], const Grid &g, const DevParams &P,
+                                                 Counters *__restrict__ cnt, const double2 *__restrict__ pos,
+                                                 uint2 *__restrict__ pair_rec, uint32_t *__restrict__ pair_off,
+                                                 uint8_t *__restrict__ pair_cnt, PS<float> *__restrict__ ps_out) {
+    const float df = (float)g.d;
+    const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
+    int K = 0;
+    SearchRec me = make_float4(0, 0, 0, 0);
+    if (live) {
+        const float hi = (df * df) * (1.0f + 4e-6f), lo = (df * df) * (1.0f - 4e-6f);
+        const uint32_t Ls = s + d0;
+        me = A.get(Ls);
+        int count = 0;
+        // FIRST .. STOP (exclusive) in local indices, walking by STEP; BY = y of this particle in the frame of the
+        // range's cell row; DELTA = local - sorted index of the range's window.  count < 20 in the loop condition =
+        // trim_collisions, collision_detector.py:91-93 (no `break`: it keeps the warp from reconverging).
+        // (Ending the walk once a candidate is more than d away in x - rows are sorted by x - was measured: the extra
+        // predicate costs what the shorter walks save.)
+#define SC_TILE_RANGE(FIRST, STOP, STEP, BY, DR, DELTA, ASC)                                                     \
+        {                                                                                                        \
+            const float by = (BY);                                                                               \
+            for (uint32_t L = (FIRST); L != (STOP) && count < SC_MAX_NEIGHBORS; L += (STEP)) {                   \
+                const SearchRec r = A.get(L);                                                                    \
+                const float dx = fmaf(r.z - me.z, df, r.x - me.x), dy = r.y - by;                                \
+                const float qd = fmaf(dx, dx, dy * dy);                                                          \
+                /* qd > hi: surely farther than d (NaN too: the reference rejects NaN); qd < lo: surely inside */ \
+                if (qd <= hi && (qd < lo || accept_exact(pos[s], pos[L - (DELTA)], g.d, (DR), (ASC)))) {         \
+                    lst.set(count, L, (uint32_t)((DR) + 1));                                                     \
+                    ++count;                                                                                     \
+                }                                                                                                \
+            }                                                                                                    \
+        }
+        SC_TILE_RANGE(Ls + 1u, b[1], 1u, me.y, 0, d0, true)
+        SC_TILE_RANGE(b[2], b[3], 1u, me.y - df, 1, d1, true)
+        SC_TILE_RANGE(Ls - 1u, b[0] - 1u, 0xFFFFFFFFu, me.y, 0, d0, false)
+        SC_TILE_RANGE(b[5] - 1u, b[4] - 1u, 0xFFFFFFFFu, me.y + df, -1, d2, false)
+#undef SC_TILE_RANGE
+        K = count;
+    }
+    // the warp's records go to one contiguous chunk of the pair buffer (one atomic per warp); where the chunk lands
+    // is arbitrary, but it is only ever reached through pair_off
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = (uint32_t)K;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&cnt->pair_cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (!live) return;
+    const uint32_t off = base + inc - (uint32_t)K;
+    pair_off[s] = off;
+    pair_cnt[s] = (uint8_t)K;
+    const uint32_t uid_s = __float_as_uint(me.w);
+    const float inv_d = (float)(1.0 / P.d);
+    const float amp = (float)(P.d * P.level);
+    float ax = 0, ay = 0, psum = 0;
+    uint2 *out = pair_rec + off;
+    for (int k = 0; k < K; ++k) {
+        uint32_t L, code;  // code = dr + 1
+        lst.get(k, L, code);
+        const SearchRec r = A.get(L);
+        float rx = fmaf(me.z - r.z, df, me.x - r.x);
+        float ry = (me.y - r.y) - fmaf((float)code, df, -df);  // the neighbor's row is dr * d further down
+        // crate.py:167-174: the neighbor's position is noised, then the unit vector from it to i and the distance
+        if constexpr (kNoise == SC_NOISE_COUNTER) {
+            float fx, fy;  // uniforms + 1
+            pair_noise_f32_1to2(pair_noise_bits(P.tick_key, uid_s, __float_as_uint(r.w)), fx, fy);
+            rx = fmaf(1.5f - fx, amp, rx);  // 0.5 - u, exact
+            ry = fmaf(1.5f - fy, amp, ry);
+        }
+        const float q = fmaf(rx, rx, ry * ry);
+        const float inv = rsqrt_ftz(q);
+        const float nx = rx * inv, ny = ry * inv;
+        const float cl = __saturatef((q * inv) * inv_d);  // np.clip(dist / d, 0, 1), crate.py:270
+        const float wgt = 1.0f - cl;
+        // one 8-byte record per directed pair: neighbor index + the unit vector as two signed 16-bit fractions
+        const int ix = __float2int_rn(nx * 32767.0f), iy = __float2int_rn(ny * 32767.0f);
+        uint32_t jrec = L;
+        if constexpr (kGlobalIdx) jrec = L - (code == 1u ? d0 : (code == 2u ? d1 : d2));
+        out[k] = make_uint2(jrec, __byte_perm((uint32_t)ix, (uint32_t)iy, 0x5410));
+        psum += wgt;
+        const float c = cl * wgt;  // (1 - w) w, crate.py:340
+        ax = fmaf(c, nx, ax);
+        ay = fmaf(c, ny, ay);
+    }
+    float p = 0;
+    if (K > 0) {
+        const float pr = psum - (float)P.ignored;
+        p = (pr > 0 || pr != pr) ? pr : 0.0f;  // np.maximum(0, pr), crate.py:273
+    }
+    PS<float> o;
+    o.p = p; o.sx = ax; o.sy = ay; o.pad_ = 0;
+    ps_out[s] = o;
+}
+
+#define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_BLOCK * 2)
+
+template <int kNoise, bool kGlobalIdx, int kRepeat = 1>
+__global__ void __launch_bounds__(SC_BLOCK, 6)
+k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
+               const BlockDesc *__restrict__ desc, const double2 *__restrict__ pos,
+               const SearchRec *__restrict__ rec, const uint32_t *__restrict__ cell_key,
+               uint2 *__restrict__ pair_rec, uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt,
+               PS<float> *__restrict__ ps_out) {
+    pdl_enter();
+    // staged: [records 20 KB | cell boundaries 5.25 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
+    __shared__ __align__(16) unsigned char s_raw[SC_TILE_SMEM_K4];
+    static_assert(SC_TILE_SMEM_K4 >= SC_MAX_NEIGHBORS * SC_BLOCK * 4, "pass-through lists must fit");
+    const uint32_t b0 = blockIdx.x * SC_BLOCK;
+    const uint32_t s = b0 + threadIdx.x;
+    // first round of loads, all independent: live count, block descriptor, own cell
+    const uint32_t n = cell_start[g.ncells];
+    if (b0 >= n) return;
+    const TileWindows w = tile_windows(desc + blockIdx.x);
+    const bool live = s < n;
+    const uint32_t c = live ? cell_key[s] : w.c_lo;
+    const uint32_t nc = (uint32_t)g.ncols;
+    uint32_t b[6];
+    if (w.staged) {
+        SearchRec *s_rec = reinterpret_cast<SearchRec *>(s_raw);
+        uint32_t *s_cs = reinterpret_cast<uint32_t *>(s_raw + SC_TILE_CAP * 16);
+        uint16_t *s_list = reinterpret_cast<uint16_t *>(s_raw + SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4);
+        // second round: the three windows and (unless the block wraps around a row end) its cell boundaries, stored
+        // as local indices
+        for (uint32_t t = threadIdx.x; t < w.total; t += SC_BLOCK) s_rec[t] = rec[tile_source(w, t)];
+        const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
+        if (w.cells_staged) {
+            const uint32_t *src = cell_start + w.c_lo - 1u;
+            for (uint32_t t = threadIdx.x; t < w.ncw; t += SC_BLOCK) {
+                s_cs[t] = src[t] + d0;
+                s_cs[SC_TILE_CELLS + t] = src[nc + t] + d1;
+                s_cs[2 * SC_TILE_CELLS + t] = (src - nc)[t] + d2;
+            }
+        } else if (live) {
+            const uint32_t *cs0 = cell_start + c - 1u;
+            b[0] = cs0[0] + d0; b[1] = cs0[3] + d0;
+            b[2] = cs0[nc] + d1; b[3] = cs0[nc + 3u] + d1;
+            b[4] = (cs0 - nc)[0] + d2; b[5] = (cs0 - nc)[3] + d2;
+        }
+        __syncthreads();
+        if (w.cells_staged) {
+            const uint32_t q = c - w.c_lo;
+            b[0] = s_cs[q]; b[1] = s_cs[q + 3u];
+            b[2] = s_cs[SC_TILE_CELLS + q]; b[3] = s_cs[SC_TILE_CELLS + q + 3u];
+            b[4] = s_cs[2 * SC_TILE_CELLS + q]; b[5] = s_cs[2 * SC_TILE_CELLS + q + 3u];
+        }
+#pragma unroll 1
+        for (int rep = 0; rep < kRepeat; ++rep)  // kRepeat > 1: developer timing aid (cost of a pass without its prologue)
+        density_particle<kNoise, kGlobalIdx>(SmemAcc<SearchRec>{smem_addr(s_rec)},
+                                             TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live, s, b, g, P, cnt, pos,
+                                             pair_rec, pair_off, pair_cnt, ps_out);
+    } else {
+        if (live) {
+            const uint32_t *cs0 = cell_start + c - 1u;
+            b[0] = cs0[0]; b[1] = cs0[3];
+            b[2] = cs0[nc]; b[3] = cs0[nc + 3u];
+            b[4] = (cs0 - nc)[0]; b[5] = (cs0 - nc)[3];
+        }
+        density_particle<kNoise, kGlobalIdx>(GmemAcc<SearchRec>{rec},
+                                             TileList<uint32_t, 28>{reinterpret_cast<uint32_t *>(s_raw) + threadIdx.x}, w,
+                                             live, s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: the neighbors' (p, s) and velocity come from the staged windows; everything after the pair loop is force_tail.
+struct PV { float4 ps; float2 v; };
+
+template <bool kMonitor, class AccPS, class AccV>
+__device__ __forceinline__ void force_particle(const AccPS &APS, const AccV &AV, uint32_t Ls, uint32_t s,
+                                               const DevParams &P, const WallParams &W,
+                                               const double2 *__restrict__ pos, const float2 *__restrict__ vel,
+                                               const uint2 *__restrict__ pair_rec,
+                                               const uint32_t *__restrict__ pair_off,
+                                               const uint8_t *__restrict__ pair_cnt,
+                                               const uint32_t *__restrict__ wall_bits,
+                                               const uint32_t *__restrict__ wall_slot,
+                                               const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out,
+                                               float2 *__restrict__ vel_out, double *__restrict__ monitor,
+                                               const uint32_t *__restrict__ n_ptr) {
+    const uint32_t off = pair_off[s];
+    const int K = pair_cnt[s];
+    const float4 me = APS.get(Ls);  // p, sx, sy
+    const float p_i = me.x;
+    const float smooth = (float)P.smooth, two_target = (float)(2 * P.target);
+    float tx = 0, ty = 0, qx = 0, qy = 0, sum_vx = 0, sum_vy = 0;
+    const uint2 *in = pair_rec + off;
+    const float fix_i = p_i - two_target;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        const uint2 r = in[k];
+        const float nx = (float)(short)(r.y & 0xFFFFu) * (1.0f / 32767.0f);
+        const float ny = (float)((int)r.y >> 16) * (1.0f / 32767.0f);
+        const float4 nb = APS.get(r.x);
+        const float2 vj = AV.get(r.x);
+        // F3 pass 2, crate.py:347-353
+        const float ddx = me.y - nb.y, ddy = me.z - nb.z;
+        const float align = fmaf(ddy, ny, ddx * nx) * smooth;
+        const float cc = align + (nb.x + fix_i);
+        tx = fmaf(cc, nx, tx);
+        ty = fmaf(cc, ny, ty);
+        // F5, crate.py:301-306
+        const float ps_ = p_i + nb.x;
+        qx = fmaf(nx, ps_, qx);
+        qy = fmaf(ny, ps_, qy);
+        sum_vx += vj.x;
+        sum_vy += vj.y;
+    }
+    force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out,
+                                vel_out, monitor, n_ptr, [&](float vx, float vy, float &ax, float &ay) {
+        ax = sum_vx - (float)K * vx;
+        ay = sum_vy - (float)K * vy;
+    });
+}
+
+template <bool kMonitor>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_force_tile(Grid g, DevParams P, const __grid_constant__ WallParams W, const uint32_t *__restrict__ cell_start,
+             const BlockDesc *__restrict__ desc, const double2 *__restrict__ pos, const float2 *__restrict__ vel,
+             const uint2 *__restrict__ pair_rec, const uint32_t *__restrict__ pair_off,
+             const uint8_t *__restrict__ pair_cnt, const PS<float> *__restrict__ ps_in,
+             const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
+             const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
+             double *__restrict__ monitor) {
+    pdl_enter();
+    __shared__ float4 s_ps[SC_TILE_CAP];
+    __shared__ float2 s_v[SC_TILE_CAP];
+    const uint32_t *n_ptr = cell_start + g.ncells;
+    const uint32_t n = *n_ptr;
+    const uint32_t b0 = blockIdx.x * SC_BLOCK;
+    if (b0 >= n) return;
+    const TileWindows w = tile_windows(desc + blockIdx.x);
+    const uint32_t s = b0 + threadIdx.x;
+    const float4 *ps4 = reinterpret_cast<const float4 *>(ps_in);
+    if (w.staged) {
+        for (uint32_t t = threadIdx.x; t < w.total; t += SC_BLOCK) {
+            const uint32_t src = tile_source(w, t);
+            s_ps[t] = ps4[src];
+            s_v[t] = vel[src];
+        }
+        __syncthreads();
+        if (s >= n) return;
+        force_particle<kMonitor>(SmemAcc<float4>{smem_addr(s_ps)}, SmemAcc<float2>{smem_addr(s_v)}, s - w.base[0], s, P,
+                                 W, pos, vel, pair_rec, pair_off, pair_cnt, wall_bits, wall_slot, wall_pre, pos_out,
+                                 vel_out, monitor, n_ptr);
+    } else {
+        if (s >= n) return;
+        force_particle<kMonitor>(GmemAcc<float4>{ps4}, GmemAcc<float2>{vel}, s, s, P, W, pos, vel, pair_rec, pair_off,
+                                 pair_cnt, wall_bits, wall_slot, wall_pre, pos_out, vel_out, monitor, n_ptr);
+    }
+}
+
+}  // namespace sc
