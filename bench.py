@@ -153,7 +153,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count()},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_sample(scene, budget_s=15.0):
@@ -183,7 +183,20 @@ def cpu_baseline_sample(scene, budget_s=15.0):
                       f"on one core in the build container (BASELINE.md section 2); it cannot run on the GPU box."}
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line, written to the process's original stdout (see main: libraries such as NCCL print banners
+    to fd 1, so everything else is sent to stderr)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # anything a library prints to stdout from here on goes to stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -407,7 +420,7 @@ def main():
         }
         if not a.no_cpu_baseline and world_size == 1:
             line["cpu_baseline"] = cpu_baseline_sample(a.scene)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 

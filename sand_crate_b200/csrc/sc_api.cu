@@ -72,6 +72,7 @@ struct sc_ctx {
     bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
     DistCfg dist{};
     WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers (+ push completion counters)
+    WireHeader *send_lo = nullptr, *send_hi = nullptr;  // the send buffers of the last sc_dist_pack (re-armed by unpack)
     unsigned push_toggle = 0;
     int64_t launches = 0;
     bool profiling = false;
@@ -1133,8 +1134,6 @@ extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_
     return 0;
 }
 
-__global__ void k_set_count(Counters *cnt) { cnt->n = cnt->n_tmp; }
-
 extern "C" int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi) {
     CKR(dist_ready(ctx, "sc_dist_set_rows"));
     if (ctx->dist.has_lo && ctx->dist.has_hi && row_hi - row_lo < 2 * (int64_t)ctx->dist.halo)
@@ -1190,37 +1189,27 @@ extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     CKR(dist_ready(ctx, "sc_dist_pack"));
     if ((ctx->dist.has_lo && !send_lo_dev) || (ctx->dist.has_hi && !send_hi_dev))
         return fail(ctx, "sc_dist_pack: a neighbor exists but its send buffer is NULL");
-    if (ctx->carry_count) {
-        ProfScope ps(ctx, SLOT_END);
-        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
-        ctx->carry_count = false;
-    }
     WireHeader *lo = send_lo_dev ? (WireHeader *)send_lo_dev : ctx->wire_dummy;
     WireHeader *hi = send_hi_dev ? (WireHeader *)send_hi_dev : ctx->wire_dummy + 1;
-    const int64_t n = ctx->n_host;
-    {
+    if (lo != ctx->send_lo || hi != ctx->send_hi) {  // first use of these buffers: arm them (later k_dist_unpack does)
         ProfScope ps(ctx, SLOT_IO);
-        k_wire_reset<<<1, 1, 0, ctx->stream>>>(lo, hi, &ctx->cnt->n_tmp);
+        k_wire_reset<<<1, 1, 0, ctx->stream>>>(lo, hi);
+        ctx->send_lo = lo; ctx->send_hi = hi;
     }
+    // the live count: the previous tick's scan total if a step ran since cnt->n was last written
+    const uint32_t *n_in = ctx->carry_count ? ctx->cell_start + ctx->grid.ncells : &ctx->cnt->n;
+    ctx->carry_count = false;
+    const int64_t n = ctx->n_host;
     if (n > 0) {
         ProfScope ps(ctx, SLOT_IO);
         if (ctx->precision == SC_PRECISION_F64)
             k_dist_pack<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, &ctx->cnt->n, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur,
-                ctx->pos_srt, (double2 *)ctx->vel_srt, ctx->uid_srt, &ctx->cnt->n_tmp, (uint32_t)ctx->cap, lo, hi);
+                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, lo, hi);
         else
             k_dist_pack<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, &ctx->cnt->n, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur,
-                ctx->pos_srt, (float2 *)ctx->vel_srt, ctx->uid_srt, &ctx->cnt->n_tmp, (uint32_t)ctx->cap, lo, hi);
-    }
-    {
-        ProfScope ps(ctx, SLOT_IO);
-        k_set_count<<<1, 1, 0, ctx->stream>>>(ctx->cnt);
+                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur, lo, hi);
     }
     CK(cudaGetLastError());
-    std::swap(ctx->pos_cur, ctx->pos_srt);
-    std::swap(ctx->vel_cur, ctx->vel_srt);
-    std::swap(ctx->uid_cur, ctx->uid_srt);
     ctx->srt_valid = false; ctx->rank_valid = false; ctx->lists_valid = false;
     ctx->n_exact = false;
     return 0;
@@ -1236,11 +1225,13 @@ static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo,
         if (ctx->precision == SC_PRECISION_F64)
             k_dist_unpack<double><<<grid, SC_BLOCK, 0, ctx->stream>>>(
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
-                (uint32_t)ctx->cap, &ctx->cnt->overflow);
+                (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
+                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1);
         else
             k_dist_unpack<float><<<grid, SC_BLOCK, 0, ctx->stream>>>(
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
-                (uint32_t)ctx->cap, &ctx->cnt->overflow);
+                (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
+                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1);
     }
     CK(cudaGetLastError());
     // the live count (owned + ghosts) is only known on the device: launch over the whole capacity, kernels exit early

@@ -41,29 +41,35 @@ __device__ __forceinline__ void wire_push(WireHeader *h, WireRec *recs, uint32_t
     recs[k] = r;
 }
 
-// counters used: cnt->n (in: particles in the *_in arrays; out: particles in the *_out arrays)
+// One read-mostly pass over the particle arrays, in place (no compaction: the arrays keep the previous tick's sorted
+// order, which is what makes the next tick's gathers nearly coalesced):
+//   last tick's ghost      -> killed: its x becomes +inf, so this tick's remove_particles pass (k_prepass) drops it
+//   row left the strip     -> MIGRANT record for the neighbor; stays here, re-tagged as a ghost, for this tick
+//   owned, near a cut      -> HALO record(s)
+// n_in_ptr = live count left by the previous tick (its scan total) or cnt->n; it is copied to cnt->n, where the
+// unpack kernel appends what the neighbors send.  The send headers' counts are zero on entry (k_dist_unpack re-arms
+// them once the previous tick's buffers have left).
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_pack(Counters *__restrict__ cnt, const uint32_t *__restrict__ n_in_ptr, Grid g, DistCfg D,
-            const double2 *__restrict__ pos_in, const typename Vec2<Real>::type *__restrict__ vel_in,
-            const uint32_t *__restrict__ uid_in, double2 *__restrict__ pos_out,
-            typename Vec2<Real>::type *__restrict__ vel_out, uint32_t *__restrict__ uid_out,
-            uint32_t *__restrict__ n_out, uint32_t out_cap, WireHeader *__restrict__ lo_hdr,
-            WireHeader *__restrict__ hi_hdr) {
+            double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
+            uint32_t *__restrict__ uid, WireHeader *__restrict__ lo_hdr, WireHeader *__restrict__ hi_hdr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_in_ptr) return;
-    (void)cnt;
-    const uint32_t u = uid_in[i];
-    if (u & SC_GHOST_BIT) return;  // last tick's ghost: its owner has the authoritative copy
-    const double2 p = pos_in[i];
-    const typename Vec2<Real>::type v = vel_in[i];
+    const uint32_t n_in = *n_in_ptr;
+    if (i == 0) cnt->n = n_in;
+    if (i >= n_in) return;
+    const uint32_t u = uid[i];
+    if (u & SC_GHOST_BIT) {  // its owner has the authoritative copy
+        pos[i].x = __longlong_as_double(0x7FF0000000000000LL);
+        return;
+    }
+    const double2 p = pos[i];
     const double fr = floor_div(p.y, g);
     const long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : 0;  // NaN: stays where it is
     WireRec *lo_recs = reinterpret_cast<WireRec *>(lo_hdr + 1), *hi_recs = reinterpret_cast<WireRec *>(hi_hdr + 1);
-    uint32_t tag = u;
     const bool below = row < D.row_lo && D.has_lo, above = row >= D.row_hi && D.has_hi;
     if (below || above) {
-        // the particle's row now belongs to a neighbor: hand it over, keep it here as a ghost for this tick
+        const typename Vec2<Real>::type v = vel[i];
         if (below) {
             if (row < D.row_lo - D.halo) lo_hdr->too_far = 1u;
             wire_push(lo_hdr, lo_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
@@ -71,16 +77,15 @@ k_dist_pack(Counters *__restrict__ cnt, const uint32_t *__restrict__ n_in_ptr, G
             if (row >= D.row_hi + D.halo) hi_hdr->too_far = 1u;
             wire_push(hi_hdr, hi_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
         }
-        tag = u | SC_GHOST_BIT;
+        uid[i] = u | SC_GHOST_BIT;
     } else {
-        if (D.has_lo && row < D.row_lo + D.halo) wire_push(lo_hdr, lo_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
-        if (D.has_hi && row >= D.row_hi - D.halo) wire_push(hi_hdr, hi_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
+        const bool to_lo = D.has_lo && row < D.row_lo + D.halo, to_hi = D.has_hi && row >= D.row_hi - D.halo;
+        if (to_lo || to_hi) {
+            const typename Vec2<Real>::type v = vel[i];
+            if (to_lo) wire_push(lo_hdr, lo_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
+            if (to_hi) wire_push(hi_hdr, hi_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
+        }
     }
-    const uint32_t k = atomicAdd(n_out, 1u);
-    if (k >= out_cap) { lo_hdr->overflow = 1u; return; }
-    pos_out[k] = p;
-    vel_out[k] = v;
-    uid_out[k] = tag;
 }
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -100,7 +105,10 @@ template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, double2 *__restrict__ pos,
               typename Vec2<Real>::type *__restrict__ vel, uint32_t *__restrict__ uid, uint32_t *__restrict__ n,
-              uint32_t cap, uint32_t *__restrict__ overflow) {
+              uint32_t cap, uint32_t *__restrict__ overflow, WireHeader *send_lo, WireHeader *send_hi) {
+    // this tick's send buffers have left (stream order): re-arm their counts for the next k_dist_pack; the sticky
+    // overflow / too_far marks stay for sc_dist_status
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { send_lo->count = 0u; send_hi->count = 0u; }
     const UnpackSide side = blockIdx.y ? hi : lo;
     if (!side.hdr) return;
     if (side.flag) {
@@ -182,10 +190,9 @@ k_dist_row_hist(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__res
     atomicAdd(&hist[row - row0], 1ull);
 }
 
-__global__ void k_wire_reset(WireHeader *a, WireHeader *b, uint32_t *n_out) {
+__global__ void k_wire_reset(WireHeader *a, WireHeader *b) {
     a->count = 0; a->overflow = 0; a->too_far = 0; a->pad_ = 0;
     b->count = 0; b->overflow = 0; b->too_far = 0; b->pad_ = 0;
-    *n_out = 0;
 }
 
 }  // namespace sc
