@@ -65,8 +65,8 @@ struct sc_ctx {
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
     bool lists_valid = false, rank_valid = false;
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
-    int pair_mode = 1;  // mixed mode with device noise: 0 = untiled K4/K5, 1 = tiled K4 + untiled K5, 2 = both tiled
-                        // (developer switch: SC_PAIR_MODE)
+    int pair_mode = 1;  // mixed mode with device noise: 1 = tiled K4 (sc_tile.cuh), 0 = the untiled K4 of sc_pair.cuh
+                        // (developer switch: SC_PAIR_MODE, for A/B timing)
     bool monitor_on = false;  // ForceMonitor mode: K5 also sums |dv| per force stage
     double *monitor = nullptr; // 6 sums + particle count of the last tick
     bool dist_on = false;     // strip decomposition: particle arrays hold owned + ghost particles
@@ -111,12 +111,33 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// launch with or without programmatic stream serialization
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_maybe_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream,
+                                    Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// Which of the strip-exchange kernels (1 pack, 2 push, 4 unpack) are launched with programmatic stream serialization.
+// Default none: with push AND unpack both launched that way an interior rank (two neighbors, direct NVLink transport)
+// hit an illegal address on 4xB200, cause not understood; every other combination passed the bit-parity check, but
+// the few microseconds are not worth an unexplained hazard.  SC_DIST_PDL overrides (developer switch).
+static int dist_pdl_mask() {
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("SC_DIST_PDL"); m = e ? atoi(e) : 0; }
+    return m;
+}
+
 static inline unsigned blocks_for(int64_t n) { return (unsigned)((n + SC_BLOCK - 1) / SC_BLOCK); }
 
 struct ProfScope {
     sc_ctx *c; int slot; cudaEvent_t e0 = nullptr, e1 = nullptr;
     ProfScope(sc_ctx *c_, int slot_) : c(c_), slot(slot_) {
-        if (slot < 0) return;  // the caller has opened a scope for this launch
         c->launches++;
         if (!c->profiling) return;
         auto get = [&]() {
@@ -128,7 +149,7 @@ struct ProfScope {
         cudaEventRecord(e0, c->stream);
     }
     ~ProfScope() {
-        if (slot < 0 || !c->profiling) return;
+        if (!c->profiling) return;
         cudaEventRecord(e1, c->stream);
         c->pending.push_back({slot, e0, e1});
     }
@@ -149,8 +170,19 @@ static int prof_flush(sc_ctx *ctx) {
     return 0;
 }
 
+// SC_POISON=<byte> (developer switch): fill every allocation with that byte, so that a read of memory nothing has
+// written shows up as garbage (0xFF: NaN / invalid index) instead of whatever a recycled allocation happened to hold
+static int poison_byte() {
+    static int b = -2;
+    if (b == -2) { const char *e = getenv("SC_POISON"); b = e ? (int)strtol(e, nullptr, 0) & 0xFF : -1; }
+    return b;
+}
 template <typename T> static int dev_alloc(sc_ctx *ctx, T **p, size_t count) {
     CK(cudaMalloc((void **)p, sizeof(T) * (count ? count : 1)));
+    if (poison_byte() >= 0) {
+        CK(cudaMemset((void *)*p, poison_byte(), sizeof(T) * (count ? count : 1)));
+        CK(cudaDeviceSynchronize());  // the fill runs on the legacy stream; the context's stream does not wait for it
+    }
     return 0;
 }
 static size_t real_size(const sc_ctx *c) { return c->precision == SC_PRECISION_F64 ? 8 : 4; }
@@ -248,7 +280,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     sc_ctx *c = new sc_ctx();
     ctx = c;
     c->device = device; c->precision = precision; c->cap = capacity;
-    { const char *e_ = getenv("SC_PAIR_MODE"); if (e_ && e_[0] >= '0' && e_[0] <= '2') c->pair_mode = e_[0] - '0'; }
+    { const char *e_ = getenv("SC_PAIR_MODE"); if (e_ && e_[0] >= '0' && e_[0] <= '1') c->pair_mode = e_[0] - '0'; }
     if (stream) c->stream = (cudaStream_t)stream;
     else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
     const size_t n = (size_t)capacity, rs = real_size(c);
@@ -631,10 +663,10 @@ static int launch_density(sc_ctx *ctx, const Grid &g, const DevParams &dp, const
 }
 
 template <typename Real>
-static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n, bool scoped = true) {
+static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n) {
     typedef typename Vec2<Real>::type R2;
-    if (scoped && ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
-    ProfScope ps(ctx, scoped ? SLOT_FORCE : -1);
+    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    ProfScope ps(ctx, SLOT_FORCE);
     auto go = [&](auto kernel) {
         return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
                           (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
@@ -645,38 +677,15 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
     return 0;
 }
 
-// mixed precision with device-side noise: the pair kernels that stage the block's neighborhood in shared memory.
-// pair_mode 1: tiled K4 + untiled K5 (records carry sorted indices); 2: both tiled (records carry local indices)
+// mixed precision with device-side noise: K4 stages the block's neighborhood in shared memory (sc_tile.cuh)
 static int launch_density_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
     auto go = [&](auto kernel) {
         return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt, g, dp, ctx->cell_start,
                           ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt, (uint2 *)ctx->pair_n,
                           ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
     };
-    const bool counter = dp.noise_mode == SC_NOISE_COUNTER;
-    if (ctx->pair_mode == 1) CK(counter ? go(k_density_tile<SC_NOISE_COUNTER, true>) : go(k_density_tile<SC_NOISE_NONE, true>));
-    else CK(counter ? go(k_density_tile<SC_NOISE_COUNTER, false>) : go(k_density_tile<SC_NOISE_NONE, false>));
+    CK(dp.noise_mode == SC_NOISE_COUNTER ? go(k_density_tile<SC_NOISE_COUNTER>) : go(k_density_tile<SC_NOISE_NONE>));
     return 0;
-}
-static int launch_force_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
-    if (ctx->pair_mode == 1) return launch_force<float>(ctx, dp, ctx->cell_start + g.ncells, n, false);
-    auto go = [&](auto kernel) {
-        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, g, dp, ctx->walls, ctx->cell_start,
-                          ctx->blk_desc, ctx->pos_srt, (const float2 *)ctx->vel_srt, (const uint2 *)ctx->pair_n,
-                          ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps, ctx->wall_bits_srt,
-                          ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->monitor);
-    };
-    CK(ctx->monitor_on ? go(k_force_tile<true>) : go(k_force_tile<false>));
-    return 0;
-}
-static int launch_tiled(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
-    {
-        ProfScope ps(ctx, SLOT_DENSITY);
-        CKR(launch_density_tile(ctx, g, dp, n));
-    }
-    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
-    ProfScope ps(ctx, SLOT_FORCE);
-    return launch_force_tile(ctx, g, dp, n);
 }
 
 static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
@@ -701,7 +710,11 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
             }
             CKR(launch_force<float>(ctx, dp, n_ptr, n));
         } else {
-            CKR(launch_tiled(ctx, g, dp, n));
+            {
+                ProfScope ps(ctx, SLOT_DENSITY);
+                CKR(launch_density_tile(ctx, g, dp, n));
+            }
+            CKR(launch_force<float>(ctx, dp, n_ptr, n));
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
@@ -1035,11 +1048,11 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
                        (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
                        (R2 *)ctx->vel_cur, ctx->monitor);
         } else if (which == 24) {
-            launch_pdl(k_density_tile<SC_NOISE_COUNTER, false, 2>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt,
+            launch_pdl(k_density_tile<SC_NOISE_COUNTER, 2>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt,
                        ctx->grid, dp, ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt,
                        (uint2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
         } else if (which == 4) { if (tiled) launch_density_tile(ctx, ctx->grid, dp, n); else launch_density<float>(ctx, ctx->grid, dp, nullptr, n); }
-        else { if (tiled) launch_force_tile(ctx, ctx->grid, dp, n); else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n); }
+        else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n);
         cudaEventRecord(e1, ctx->stream);
         cudaEventSynchronize(e1);
         float ms = 0;
@@ -1203,11 +1216,11 @@ extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     if (n > 0) {
         ProfScope ps(ctx, SLOT_IO);
         if (ctx->precision == SC_PRECISION_F64)
-            k_dist_pack<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, lo, hi);
+            CK(launch_maybe_pdl(dist_pdl_mask() & 1, k_dist_pack<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
+                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, lo, hi));
         else
-            k_dist_pack<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(
-                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur, lo, hi);
+            CK(launch_maybe_pdl(dist_pdl_mask() & 1, k_dist_pack<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
+                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur, lo, hi));
     }
     CK(cudaGetLastError());
     ctx->srt_valid = false; ctx->rank_valid = false; ctx->lists_valid = false;
@@ -1223,15 +1236,15 @@ static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo,
         ProfScope ps(ctx, SLOT_IO);
         const dim3 grid(blocks_for(ctx->dist.cap), 2);
         if (ctx->precision == SC_PRECISION_F64)
-            k_dist_unpack<double><<<grid, SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<double>, grid, dim3(SC_BLOCK), ctx->stream,
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
                 (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
-                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1);
+                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1));
         else
-            k_dist_unpack<float><<<grid, SC_BLOCK, 0, ctx->stream>>>(
+            CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<float>, grid, dim3(SC_BLOCK), ctx->stream,
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
                 (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
-                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1);
+                ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1));
     }
     CK(cudaGetLastError());
     // the live count (owned + ghosts) is only known on the device: launch over the whole capacity, kernels exit early
@@ -1268,7 +1281,7 @@ extern "C" int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_rec
     ProfScope ps(ctx, SLOT_IO);
     const size_t bytes = sizeof(WireHeader) + (size_t)ctx->dist.cap * sizeof(WireRec);
     const unsigned nb = (unsigned)std::min<size_t>((bytes / 16 + SC_BLOCK - 1) / SC_BLOCK, 64);
-    k_wire_push<<<dim3(nb, 2), SC_BLOCK, 0, ctx->stream>>>(lo, hi, ctx->dist.cap, value);
+    CK(launch_maybe_pdl(dist_pdl_mask() & 2, k_wire_push, dim3(nb, 2), dim3(SC_BLOCK), ctx->stream, lo, hi, ctx->dist.cap, value));
     CK(cudaGetLastError());
     return 0;
 }

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_pack(Counters *__restrict__ cnt, const uint32_t *__restrict__ n_in_ptr, Grid g, DistCfg D,
             double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
             uint32_t *__restrict__ uid, WireHeader *__restrict__ lo_hdr, WireHeader *__restrict__ hi_hdr) {
+    pdl_enter();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
     if (i == 0) cnt->n = n_in;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, double2 *__restrict__ pos,
               typename Vec2<Real>::type *__restrict__ vel, uint32_t *__restrict__ uid, uint32_t *__restrict__ n,
               uint32_t cap, uint32_t *__restrict__ overflow, WireHeader *send_lo, WireHeader *send_hi) {
+    pdl_enter();
     // this tick's send buffers have left (stream order): re-arm their counts for the next k_dist_pack; the sticky
     // overflow / too_far marks stay for sc_dist_status
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { send_lo->count = 0u; send_hi->count = 0u; }
@@ -156,6 +158,7 @@ struct PushSide { const WireHeader *src; void *peer_dst; uint32_t *peer_flag; ui
 
 __global__ void __launch_bounds__(SC_BLOCK)
 k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
+    pdl_enter();
     const PushSide side = blockIdx.y ? hi : lo;
     if (!side.src) return;
     const uint32_t count = side.src->count < cap ? side.src->count : cap;

@@ -241,7 +241,6 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
           uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, PS<Real> *__restrict__ ps_out) {
     pdl_enter();
     __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
-    __shared__ uint32_t s_base;
     const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = s < n;
@@ -452,6 +451,7 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
 // K5: all forces, wall bounce, continuous collision and integration for particle s
 // kMonitor: also accumulate, per force stage, the sum over particles of |dv| (the reference's ForceMonitor,
 // utils/force_monitor.py:23-33, wraps exactly these six stages: crate.py:110-124)
+// occupancy hint for K5 (forcing 5 or 6 blocks per SM spills the fp64 wall / crossing code: measured 2-8 us slower)
 #ifndef SC_K5_MINBLOCKS
 #define SC_K5_MINBLOCKS 1
 #endif

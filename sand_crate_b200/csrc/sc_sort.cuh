@@ -14,11 +14,11 @@ namespace sc {
 //   kStep = true : remove_particles (crate.py:149-159), calc_virtual_colliders + apply_hard_wall_fix
 //                  (crate.py:213-243, 202-211), then the cell key
 //   kStep = false: cell key only (standalone detect_particle_collisions)
+// particles per thread: the kernel is a chain of two long-latency operations (position load, histogram atomic), so
+// independent chains are interleaved (4 measured the same as 2)
 #ifndef SC_PREPASS_ILP
 #define SC_PREPASS_ILP 2
 #endif
-//                     ^ // particles per thread: the kernel is a chain of two long-latency operations (position
-                          // load, histogram atomic), so independent chains are interleaved
 template <bool kStep>
 __global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it is rare
 k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
@@ -98,10 +98,10 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
 // exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply).
 // 16 items per thread as four 128-bit accesses: a warp request covers 2 KB contiguous.
 #define SC_SCAN_ITEMS 16
+// few, large tiles (256- and 512-thread tiles measured 2-4 us slower on the 1.8M-cell grid)
 #ifndef SC_SCAN_THREADS
 #define SC_SCAN_THREADS 1024
 #endif
-//                      ^ // few, large tiles: the look-back of tile k walks k / 32 windows when all start together
 #define SC_SCAN_TILE (SC_SCAN_THREADS * SC_SCAN_ITEMS)
 
 __device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {

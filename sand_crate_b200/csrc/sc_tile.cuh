@@ -1,5 +1,5 @@
-// sc_tile.cuh - the production (mixed precision, device noise) pair kernels: K4 and K5 with the neighborhood of a
-// block staged in shared memory.
+// sc_tile.cuh - the production (mixed precision, device noise) density kernel: K4 with the neighborhood of a block
+// staged in shared memory.
 //
 // A block owns SC_BLOCK consecutive particles of the sorted set.  Because the sort is cell-major (row, col, x), every
 // neighbor of those particles lies in one of three CONTIGUOUS windows of the sorted set - the block's own stretch of
@@ -9,19 +9,23 @@
 //     W1 = [cell_start[c_lo + ncols - 1], cell_start[c_hi + ncols + 2])   next row(s)
 //     W2 = [cell_start[c_lo - ncols - 1], cell_start[c_hi - ncols + 2])   previous row(s)
 //
-// (c_lo, c_hi = cells of the block's first / last particle).  The windows are copied into shared memory once with
-// coalesced 16-byte loads; the candidate loop (K4) and the neighbor gathers (K5) then read shared memory instead of
-// issuing one dependent global load per candidate / per pair.  A staged particle is addressed by its position in the
-// concatenation W0 | W1 | W2 ("local index"); K4 writes local indices into the pair records, and K5, which cuts the
-// sorted set into the same blocks, stages the same windows and resolves them without any translation.
+// (c_lo, c_hi = cells of the block's first / last particle; k_rank_gather leaves the six bounds in a per-block
+// descriptor, so the kernel starts with ONE dependent load instead of a chain of four).  The windows and the block's
+// slice of the cell boundaries are copied into shared memory with coalesced loads; the candidate loop then reads
+// 16-byte records (cell-relative position, cell column, uid) from shared memory instead of issuing a dependent global
+// load per candidate.  A staged particle is addressed by its position in the concatenation W0 | W1 | W2 ("local
+// index", 11 bits), so the per-thread neighbor lists are 16-bit.
 //
 // When the three windows do not fit the staging buffer (a block of spray that spans many sparse rows), the block
 // runs the same code with a pass-through accessor: local index = sorted index, reads go to global memory.  The
 // arithmetic is identical in both modes, so a particle's result does not depend on which mode its block ran in
 // (the strip decomposition relies on that: a ghost and its owner must compute the same bits).
 //
-// What the kernels compute is what sc_pair.cuh computes (same reference lines, same list order, same 20-trim, same
-// fp32-screen / fp64-replay acceptance); only the data movement differs.
+// What the kernel computes is what k_density in sc_pair.cuh computes (same reference lines, same list order, same
+// 20-trim, same fp32-screen / fp64-replay acceptance); only the data movement differs.  Measured on B200 (dam-break
+// 1M): 69 -> 59 us.  The same staging for K5 (neighbor pressure / normal / velocity from shared memory instead of
+// gathers) was built and measured SLOWER than the gathering kernel (60 vs 46 us: K5 does too little work per staged
+// byte to pay for the extra barrier and the 3x staging traffic), so K5 stays untiled and reads sorted indices.
 #pragma once
 #include "sc_pair.cuh"
 
@@ -111,8 +115,8 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 // ------------------------------------------------------------------------------------------------------------
 // K4 body for one particle.  s = sorted index; b[] = the six boundaries of its four candidate ranges as LOCAL
 // indices (m0, m3 | n0, n3 | p0, p3 of collect_neighbors, shifted into the staged windows).  List order = reference
-// list order.  kGlobalIdx: the pair records carry sorted indices (consumed by the untiled K5) instead of local ones.
-template <int kNoise, bool kGlobalIdx, class Acc, class List>
+// list order.  The pair records carry SORTED indices (K5 gathers from global memory).
+template <int kNoise, class Acc, class List>
 __device__ __forceinline__ void density_particle(const Acc &A, List lst, const TileWindows &w, bool live, uint32_t s,
                                                  const uint32_t (&b)[6], const Grid &g, const DevParams &P,
                                                  Counters *__restrict__ cnt, const double2 *__restrict__ pos,
@@ -195,8 +199,7 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         const float wgt = 1.0f - cl;
         // one 8-byte record per directed pair: neighbor index + the unit vector as two signed 16-bit fractions
         const int ix = __float2int_rn(nx * 32767.0f), iy = __float2int_rn(ny * 32767.0f);
-        uint32_t jrec = L;
-        if constexpr (kGlobalIdx) jrec = L - (code == 1u ? d0 : (code == 2u ? d1 : d2));
+        const uint32_t jrec = L - (code == 1u ? d0 : (code == 2u ? d1 : d2));
         out[k] = make_uint2(jrec, __byte_perm((uint32_t)ix, (uint32_t)iy, 0x5410));
         psum += wgt;
         const float c = cl * wgt;  // (1 - w) w, crate.py:340
@@ -215,7 +218,7 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
 
 #define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_BLOCK * 2)
 
-template <int kNoise, bool kGlobalIdx, int kRepeat = 1>
+template <int kNoise, int kRepeat = 1>
 __global__ void __launch_bounds__(SC_BLOCK, 6)
 k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
                const BlockDesc *__restrict__ desc, const double2 *__restrict__ pos,
@@ -266,7 +269,7 @@ k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *
         }
 #pragma unroll 1
         for (int rep = 0; rep < kRepeat; ++rep)  // kRepeat > 1: developer timing aid (cost of a pass without its prologue)
-        density_particle<kNoise, kGlobalIdx>(SmemAcc<SearchRec>{smem_addr(s_rec)},
+        density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr(s_rec)},
                                              TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live, s, b, g, P, cnt, pos,
                                              pair_rec, pair_off, pair_cnt, ps_out);
     } else {
@@ -276,97 +279,9 @@ k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *
             b[2] = cs0[nc]; b[3] = cs0[nc + 3u];
             b[4] = (cs0 - nc)[0]; b[5] = (cs0 - nc)[3];
         }
-        density_particle<kNoise, kGlobalIdx>(GmemAcc<SearchRec>{rec},
+        density_particle<kNoise>(GmemAcc<SearchRec>{rec},
                                              TileList<uint32_t, 28>{reinterpret_cast<uint32_t *>(s_raw) + threadIdx.x}, w,
                                              live, s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K5: the neighbors' (p, s) and velocity come from the staged windows; everything after the pair loop is force_tail.
-struct PV { float4 ps; float2 v; };
-
-template <bool kMonitor, class AccPS, class AccV>
-__device__ __forceinline__ void force_particle(const AccPS &APS, const AccV &AV, uint32_t Ls, uint32_t s,
-                                               const DevParams &P, const WallParams &W,
-                                               const double2 *__restrict__ pos, const float2 *__restrict__ vel,
-                                               const uint2 *__restrict__ pair_rec,
-                                               const uint32_t *__restrict__ pair_off,
-                                               const uint8_t *__restrict__ pair_cnt,
-                                               const uint32_t *__restrict__ wall_bits,
-                                               const uint32_t *__restrict__ wall_slot,
-                                               const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out,
-                                               float2 *__restrict__ vel_out, double *__restrict__ monitor,
-                                               const uint32_t *__restrict__ n_ptr) {
-    const uint32_t off = pair_off[s];
-    const int K = pair_cnt[s];
-    const float4 me = APS.get(Ls);  // p, sx, sy
-    const float p_i = me.x;
-    const float smooth = (float)P.smooth, two_target = (float)(2 * P.target);
-    float tx = 0, ty = 0, qx = 0, qy = 0, sum_vx = 0, sum_vy = 0;
-    const uint2 *in = pair_rec + off;
-    const float fix_i = p_i - two_target;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        const uint2 r = in[k];
-        const float nx = (float)(short)(r.y & 0xFFFFu) * (1.0f / 32767.0f);
-        const float ny = (float)((int)r.y >> 16) * (1.0f / 32767.0f);
-        const float4 nb = APS.get(r.x);
-        const float2 vj = AV.get(r.x);
-        // F3 pass 2, crate.py:347-353
-        const float ddx = me.y - nb.y, ddy = me.z - nb.z;
-        const float align = fmaf(ddy, ny, ddx * nx) * smooth;
-        const float cc = align + (nb.x + fix_i);
-        tx = fmaf(cc, nx, tx);
-        ty = fmaf(cc, ny, ty);
-        // F5, crate.py:301-306
-        const float ps_ = p_i + nb.x;
-        qx = fmaf(nx, ps_, qx);
-        qy = fmaf(ny, ps_, qy);
-        sum_vx += vj.x;
-        sum_vy += vj.y;
-    }
-    force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out,
-                                vel_out, monitor, n_ptr, [&](float vx, float vy, float &ax, float &ay) {
-        ax = sum_vx - (float)K * vx;
-        ay = sum_vy - (float)K * vy;
-    });
-}
-
-template <bool kMonitor>
-__global__ void __launch_bounds__(SC_BLOCK)
-k_force_tile(Grid g, DevParams P, const __grid_constant__ WallParams W, const uint32_t *__restrict__ cell_start,
-             const BlockDesc *__restrict__ desc, const double2 *__restrict__ pos, const float2 *__restrict__ vel,
-             const uint2 *__restrict__ pair_rec, const uint32_t *__restrict__ pair_off,
-             const uint8_t *__restrict__ pair_cnt, const PS<float> *__restrict__ ps_in,
-             const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
-             const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out, float2 *__restrict__ vel_out,
-             double *__restrict__ monitor) {
-    pdl_enter();
-    __shared__ float4 s_ps[SC_TILE_CAP];
-    __shared__ float2 s_v[SC_TILE_CAP];
-    const uint32_t *n_ptr = cell_start + g.ncells;
-    const uint32_t n = *n_ptr;
-    const uint32_t b0 = blockIdx.x * SC_BLOCK;
-    if (b0 >= n) return;
-    const TileWindows w = tile_windows(desc + blockIdx.x);
-    const uint32_t s = b0 + threadIdx.x;
-    const float4 *ps4 = reinterpret_cast<const float4 *>(ps_in);
-    if (w.staged) {
-        for (uint32_t t = threadIdx.x; t < w.total; t += SC_BLOCK) {
-            const uint32_t src = tile_source(w, t);
-            s_ps[t] = ps4[src];
-            s_v[t] = vel[src];
-        }
-        __syncthreads();
-        if (s >= n) return;
-        force_particle<kMonitor>(SmemAcc<float4>{smem_addr(s_ps)}, SmemAcc<float2>{smem_addr(s_v)}, s - w.base[0], s, P,
-                                 W, pos, vel, pair_rec, pair_off, pair_cnt, wall_bits, wall_slot, wall_pre, pos_out,
-                                 vel_out, monitor, n_ptr);
-    } else {
-        if (s >= n) return;
-        force_particle<kMonitor>(GmemAcc<float4>{ps4}, GmemAcc<float2>{vel}, s, s, P, W, pos, vel, pair_rec, pair_off,
-                                 pair_cnt, wall_bits, wall_slot, wall_pre, pos_out, vel_out, monitor, n_ptr);
     }
 }
 

@@ -31,9 +31,12 @@ def main():
     torch.cuda.set_stream(stream)
     ok = True
     transport = os.environ.get("SC_TRANSPORT", "nccl")
-    for maker, n, ticks, precision, rebalance in ((dam_break, 200_000, 12, "f64", 0), (box_fill, 300_000, 8, "f64", 0),
-                                                  (dam_break, 200_000, 12, "mixed", 0),
-                                                  (dam_break, 200_000, 16, "f64", 3)):
+    cases = ((dam_break, 200_000, 12, "f64", 0), (box_fill, 300_000, 8, "f64", 0),
+             (dam_break, 200_000, 12, "mixed", 0), (dam_break, 200_000, 16, "f64", 3))
+    only = os.environ.get("SC_CHECK_ONLY")  # developer aid: run some of the cases, by index ("2,3")
+    if only is not None:
+        cases = tuple(cases[int(k)] for k in only.split(","))
+    for maker, n, ticks, precision, rebalance in cases:
         world_cfg, pos, vel = maker(n)
         cuts = None
         if rebalance:  # start from the equal-count cuts of ANOTHER scene (the column 0.1 higher): unbalanced here
@@ -61,6 +64,15 @@ def main():
             single.step(ticks)
             suid, sp, sv = single.gather()
             same = np.array_equal(uid, suid) and np.array_equal(gp, sp) and np.array_equal(gv, sv)
+            if not same:  # say what differs
+                if not np.array_equal(uid, suid):
+                    u, c = np.unique(uid, return_counts=True)
+                    print(f"[mgpu]   uid sets differ: {len(uid)} vs {len(suid)}, duplicated {int((c > 1).sum())}, "
+                          f"missing {len(np.setdiff1d(suid, uid))}", flush=True)
+                else:
+                    bad = np.nonzero(np.any(gp != sp, 1) | np.any(gv != sv, 1))[0]
+                    print(f"[mgpu]   {len(bad)} particles differ, max |dpos| {np.abs(gp - sp).max():.3e}, "
+                          f"max |dvel| {np.abs(gv - sv).max():.3e}", flush=True)
             flags = any(s["overflow"] or s["too_far"] for _, s in moved_all)
             print(f"[mgpu] transport={transport} {maker.__name__} n={n} ticks={ticks} {precision} ranks={world}: "
                   f"bit-identical to single GPU = {same}; migrated = {[m for m, _ in moved_all]}; "
