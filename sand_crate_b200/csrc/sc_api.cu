@@ -1063,6 +1063,16 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
     return total / reps;
 }
 
+// developer aid: how many blocks of the tiled density kernel took the pass-through path in the last tick
+extern "C" int64_t sc_debug_untiled_blocks(sc_ctx *ctx) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    Counters h;
+    if (cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)h.n_untiled;
+}
+
 // ---- ForceMonitor (utils/force_monitor.py) ------------------------------------------------------------------------
 extern "C" int sc_set_monitor(sc_ctx *ctx, int on) {
     if (!ctx) return fail(ctx, "sc_set_monitor: NULL ctx");

@@ -5,6 +5,9 @@
 //   sc_kernels_f64.cu  (-fmad=false)  Real = double: NumPy never fuses multiply-add, so neither may we
 //   sc_kernels_f32.cu                 Real = float : production mode, positions stay fp64 in HBM
 #pragma once
+#ifdef SC_NO_RESTRICT
+#define
+#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -15,6 +18,13 @@
 
 namespace sc {
 
+// NO POINTER IN THIS LIBRARY IS DECLARED __restrict__.  With `const T *__restrict__` nvcc turns loads into
+// ld.global.nc (LDG.E.CONSTANT), the non-coherent path, which is only defined for data that is read-only for the whole
+// lifetime of the kernel.  Under programmatic dependent launch (below) a kernel's blocks are resident BEFORE the
+// preceding kernel has finished writing that data, so non-coherent loads could (and, measured on B200, did) return
+// stale lines: fp64 free runs were not reproducible from run to run and occasionally faulted, and went away with
+// CUDA_LAUNCH_BLOCKING=1.  Plain loads are ordered by griddepcontrol.wait; they cost nothing measurable here.
+//
 // Programmatic dependent launch (sm_90+): the step's kernels are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's blocks may become resident while the
 // current kernel drains.  pdl_enter() = let the dependent kernel start launching, then wait until everything the
@@ -72,7 +82,7 @@ struct Counters {
     uint32_t overflow;   // capacity problems seen on the device
     uint32_t pair_cursor;  // next free record of the pair buffer (bump allocator, reset every tick)
     uint32_t n_tmp;        // scratch count (strip decomposition pack / readback)
-    uint32_t pad_[1];
+    uint32_t n_untiled;    // blocks of the tiled K4 that ran in pass-through mode this tick (windows too large to stage)
 };
 
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------

@@ -51,9 +51,9 @@ __device__ __forceinline__ void wire_push(WireHeader *h, WireRec *recs, uint32_t
 // them once the previous tick's buffers have left).
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_dist_pack(Counters *__restrict__ cnt, const uint32_t *__restrict__ n_in_ptr, Grid g, DistCfg D,
-            double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
-            uint32_t *__restrict__ uid, WireHeader *__restrict__ lo_hdr, WireHeader *__restrict__ hi_hdr) {
+k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D,
+            double2 *pos, const typename Vec2<Real>::type *vel,
+            uint32_t *uid, WireHeader *lo_hdr, WireHeader *hi_hdr) {
     pdl_enter();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
@@ -104,9 +104,9 @@ struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == 
 // waits for its side's flag to reach `value` (raised by the neighbor's k_wire_push, which runs on another GPU).
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, double2 *__restrict__ pos,
-              typename Vec2<Real>::type *__restrict__ vel, uint32_t *__restrict__ uid, uint32_t *__restrict__ n,
-              uint32_t cap, uint32_t *__restrict__ overflow, WireHeader *send_lo, WireHeader *send_hi) {
+k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, double2 *pos,
+              typename Vec2<Real>::type *vel, uint32_t *uid, uint32_t *n,
+              uint32_t cap, uint32_t *overflow, WireHeader *send_lo, WireHeader *send_hi) {
     pdl_enter();
     // this tick's send buffers have left (stream order): re-arm their counts for the next k_dist_pack; the sticky
     // overflow / too_far marks stay for sc_dist_status
@@ -134,10 +134,10 @@ k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, d
 // owned particles (no ghosts) compacted into staging arrays for readback; order is arbitrary, uids identify rows
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_dist_collect_owned(const uint32_t *__restrict__ n_ptr, const double2 *__restrict__ pos,
-                     const typename Vec2<Real>::type *__restrict__ vel, const uint32_t *__restrict__ uid,
-                     double2 *__restrict__ pos_out, double2 *__restrict__ vel_out, uint32_t *__restrict__ uid_out,
-                     uint32_t *__restrict__ n_out) {
+k_dist_collect_owned(const uint32_t *n_ptr, const double2 *pos,
+                     const typename Vec2<Real>::type *vel, const uint32_t *uid,
+                     double2 *pos_out, double2 *vel_out, uint32_t *uid_out,
+                     uint32_t *n_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     const uint32_t u = uid[i];
@@ -182,8 +182,8 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
 // per-row counts of the owned particles (input of the partition re-cut): hist[row - row0], rows outside are clamped
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_dist_row_hist(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__restrict__ pos,
-                const uint32_t *__restrict__ uid, long long row0, int nrows, unsigned long long *__restrict__ hist) {
+k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
+                const uint32_t *uid, long long row0, int nrows, unsigned long long *hist) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     if (uid[i] & SC_GHOST_BIT) return;

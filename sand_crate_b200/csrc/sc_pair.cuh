@@ -55,8 +55,8 @@ static __device__ __noinline__ bool accept_exact(double2 ps, double2 pj, double 
 //   forward : (0,0) beyond s, (0,+1), (+1,-1), (+1,0), (+1,+1)   ascending
 //   backward: (0,0) before s, (0,-1), (-1,+1), (-1,0), (-1,-1)   descending            [(dr, dc), mirrored]
 __device__ __forceinline__ int collect_neighbors(uint32_t s, uint32_t c, const Grid &g,
-                                                 const uint32_t *__restrict__ cell_start,
-                                                 const float2 *__restrict__ rel, const double2 *__restrict__ pos,
+                                                 const uint32_t *cell_start,
+                                                 const float2 *rel, const double2 *pos,
                                                  NbrList lst) {
     const float df = (float)g.d;
     const float hi = (df * df) * (1.0f + 4e-6f), lo = (df * df) * (1.0f - 4e-6f);
@@ -105,7 +105,7 @@ template <typename Real> struct PairGeom { Real nx, ny, w; };
 
 template <int kNoise>
 __device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, double2 pi, double2 pj, uint32_t uid_i,
-                                                          uint32_t uid_j, const double *__restrict__ host_noise,
+                                                          uint32_t uid_j, const double *host_noise,
                                                           uint32_t noise_index) {
     double qx = pj.x, qy = pj.y;
     if constexpr (kNoise != SC_NOISE_NONE) {
@@ -137,7 +137,7 @@ __device__ __forceinline__ PairGeom<double> pair_geom_f64(const DevParams &P, do
 // 1e-4-level precision in the weights at d ~ 1e-4)
 template <int kNoise>
 __device__ __forceinline__ PairGeom<float> pair_geom_f32(const DevParams &P, float rx, float ry, uint32_t uid_i,
-                                                         uint32_t uid_j, const double *__restrict__ host_noise,
+                                                         uint32_t uid_j, const double *host_noise,
                                                          uint32_t noise_index) {
     if constexpr (kNoise != SC_NOISE_NONE) {
         float ux, uy;
@@ -233,12 +233,12 @@ __device__ inline double np_sum_1d(const double *a, int n) {
 // good trade.
 template <typename Real, int kNoise>  // kNoise: SC_NOISE_* resolved at compile time (no branch in the pair loop)
 __global__ void __launch_bounds__(SC_BLOCK)
-k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
-          const double2 *__restrict__ pos, const float2 *__restrict__ rel, const uint32_t *__restrict__ cell_key,
-          const uint32_t *__restrict__ uid, const double *__restrict__ host_noise,
-          const uint32_t *__restrict__ noise_off, const uint32_t *__restrict__ rank_of_uid,
-          uint32_t *__restrict__ pair_j, typename Vec2<Real>::type *__restrict__ pair_n,
-          uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt, PS<Real> *__restrict__ ps_out) {
+k_density(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
+          const double2 *pos, const float2 *rel, const uint32_t *cell_key,
+          const uint32_t *uid, const double *host_noise,
+          const uint32_t *noise_off, const uint32_t *rank_of_uid,
+          uint32_t *pair_j, typename Vec2<Real>::type *pair_n,
+          uint32_t *pair_off, uint8_t *pair_cnt, PS<Real> *ps_out) {
     pdl_enter();
     __shared__ uint32_t s_list[SC_MAX_NEIGHBORS * SC_BLOCK];
     const uint32_t n = cell_start[g.ncells];
@@ -312,13 +312,13 @@ k_density(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__res
 // bounce, continuous collision, integration.  `visc(vx, vy, ax, ay)` supplies sum_j (v_j - v) (crate.py:319-323).
 template <typename Real, bool kMonitor, bool kNoRare = false, typename ViscFn>
 __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx, Real ty, Real qx, Real qy,
-                                           const DevParams &P, const WallParams &W, const double2 *__restrict__ pos,
-                                           const typename Vec2<Real>::type *__restrict__ vel,
-                                           const uint32_t *__restrict__ wall_bits,
-                                           const uint32_t *__restrict__ wall_slot,
-                                           const double2 *__restrict__ wall_pre, double2 *__restrict__ pos_out,
-                                           typename Vec2<Real>::type *__restrict__ vel_out,
-                                           double *__restrict__ monitor, const uint32_t *__restrict__ n_ptr,
+                                           const DevParams &P, const WallParams &W, const double2 *pos,
+                                           const typename Vec2<Real>::type *vel,
+                                           const uint32_t *wall_bits,
+                                           const uint32_t *wall_slot,
+                                           const double2 *wall_pre, double2 *pos_out,
+                                           typename Vec2<Real>::type *vel_out,
+                                           double *monitor, const uint32_t *n_ptr,
                                            ViscFn visc) {
     typedef typename Vec2<Real>::type R2;
     double mon[6] = {0, 0, 0, 0, 0, 0};
@@ -457,14 +457,14 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
 #endif
 template <typename Real, bool kMonitor, bool kNoRare = false>  // kNoRare: developer timing aid (wrong results)
 __global__ void __launch_bounds__(SC_BLOCK, SC_K5_MINBLOCKS)
-k_force(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
-        const double2 *__restrict__ pos, const typename Vec2<Real>::type *__restrict__ vel,
-        const uint32_t *__restrict__ pair_j, const typename Vec2<Real>::type *__restrict__ pair_n,
-        const uint32_t *__restrict__ pair_off, const uint8_t *__restrict__ pair_cnt,
-        const PS<Real> *__restrict__ ps_in, const uint32_t *__restrict__ wall_bits,
-        const uint32_t *__restrict__ wall_slot, const double2 *__restrict__ wall_pre,
-        double2 *__restrict__ pos_out, typename Vec2<Real>::type *__restrict__ vel_out,
-        double *__restrict__ monitor) {
+k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W,
+        const double2 *pos, const typename Vec2<Real>::type *vel,
+        const uint32_t *pair_j, const typename Vec2<Real>::type *pair_n,
+        const uint32_t *pair_off, const uint8_t *pair_cnt,
+        const PS<Real> *ps_in, const uint32_t *wall_bits,
+        const uint32_t *wall_slot, const double2 *wall_pre,
+        double2 *pos_out, typename Vec2<Real>::type *vel_out,
+        double *monitor) {
     pdl_enter();
     typedef typename Vec2<Real>::type R2;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;

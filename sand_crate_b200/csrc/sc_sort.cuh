@@ -21,10 +21,10 @@ namespace sc {
 #endif
 template <bool kStep>
 __global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it is rare
-k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
-          double2 *__restrict__ pos, uint32_t *__restrict__ cell_key, uint32_t *__restrict__ slot,
-          uint32_t *__restrict__ cell_count, uint32_t *__restrict__ wall_bits, uint32_t *__restrict__ wall_slot,
-          double2 *__restrict__ wall_pre) {
+k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
+          double2 *pos, uint32_t *cell_key, uint32_t *slot,
+          uint32_t *cell_count, uint32_t *wall_bits, uint32_t *wall_slot,
+          double2 *wall_pre) {
     pdl_enter();
     const uint32_t n = cnt->n;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
@@ -104,7 +104,7 @@ k_prepass(Counters *__restrict__ cnt, Grid g, DevParams P, const __grid_constant
 #endif
 #define SC_SCAN_TILE (SC_SCAN_THREADS * SC_SCAN_ITEMS)
 
-__device__ __forceinline__ void scan_load(const uint32_t *__restrict__ a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {
+__device__ __forceinline__ void scan_load(const uint32_t *a, uint32_t n, uint32_t base, uint32_t (&item)[SC_SCAN_ITEMS]) {
     if (base + SC_SCAN_ITEMS <= n) {
         const uint4 *p = reinterpret_cast<const uint4 *>(a + base);  // base is a multiple of 16 items
 #pragma unroll
@@ -131,8 +131,8 @@ __device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long lon
 }
 
 __global__ void __launch_bounds__(SC_SCAN_THREADS)
-k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__restrict__ desc,
-                uint32_t *__restrict__ ticket) {
+k_scan_lookback(uint32_t *a, uint32_t n, unsigned long long *desc,
+                uint32_t *ticket) {
     pdl_enter();
     __shared__ uint32_t s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
@@ -184,8 +184,8 @@ k_scan_lookback(uint32_t *__restrict__ a, uint32_t n, unsigned long long *__rest
 // is arbitrary here; k_rank_gather makes it deterministic.
 #define SC_PLACE_ILP 4
 __global__ void __launch_bounds__(SC_BLOCK)
-k_place(const Counters *__restrict__ cnt, const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ slot,
-        const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ tmpidx) {
+k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
+        const uint32_t *cell_start, uint32_t *tmpidx) {
     pdl_enter();
     const uint32_t n = cnt->n;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
@@ -208,14 +208,14 @@ k_place(const Counters *__restrict__ cnt, const uint32_t *__restrict__ cell_key,
 // Produces exactly np.lexsort((x, floor(y / d))) (collision_detector.py:127) as the concatenation of cells.
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ tmpidx,
-              const uint32_t *__restrict__ cell_key, const double2 *__restrict__ pos,
-              const typename Vec2<Real>::type *__restrict__ vel, const uint32_t *__restrict__ uid,
-              const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
-              double2 *__restrict__ pos_s, float2 *__restrict__ rel_s,
-              typename Vec2<Real>::type *__restrict__ vel_s, uint32_t *__restrict__ uid_s,
-              uint32_t *__restrict__ cell_key_s, uint32_t *__restrict__ wall_bits_s,
-              uint32_t *__restrict__ wall_slot_s, SearchRec *__restrict__ rec_s, BlockDesc *__restrict__ desc) {
+k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
+              const uint32_t *cell_key, const double2 *pos,
+              const typename Vec2<Real>::type *vel, const uint32_t *uid,
+              const uint32_t *wall_bits, const uint32_t *wall_slot,
+              double2 *pos_s, float2 *rel_s,
+              typename Vec2<Real>::type *vel_s, uint32_t *uid_s,
+              uint32_t *cell_key_s, uint32_t *wall_bits_s,
+              uint32_t *wall_slot_s, SearchRec *rec_s, BlockDesc *desc) {
     pdl_enter();
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,7 +266,7 @@ k_rank_gather(Grid g, const uint32_t *__restrict__ cell_start, const uint32_t *_
 // ------------------------------------------------------------------------------------------------------------
 // uid -> rank among live particles (= the reference's row index, crate.py:146-159)
 __global__ void __launch_bounds__(SC_BLOCK)
-k_mark_alive(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid, uint32_t *__restrict__ alive) {
+k_mark_alive(const uint32_t *n_ptr, const uint32_t *uid, uint32_t *alive) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     alive[uid[s]] = 1u;
@@ -274,11 +274,11 @@ k_mark_alive(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ ui
 
 // neighbor counts (and optionally lists, as sorted indices) - the parity tap and the SC_NOISE_HOST split step
 __global__ void __launch_bounds__(SC_BLOCK)
-k_count_neighbors(Counters *__restrict__ cnt, Grid g, const uint32_t *__restrict__ cell_start,
-                  const double2 *__restrict__ pos, const float2 *__restrict__ rel,
-                  const uint32_t *__restrict__ cell_key, const uint32_t *__restrict__ uid,
-                  const uint32_t *__restrict__ rank_of_uid, uint32_t *__restrict__ count_by_rank,
-                  uint32_t *__restrict__ list_sorted) {
+k_count_neighbors(Counters *cnt, Grid g, const uint32_t *cell_start,
+                  const double2 *pos, const float2 *rel,
+                  const uint32_t *cell_key, const uint32_t *uid,
+                  const uint32_t *rank_of_uid, uint32_t *count_by_rank,
+                  uint32_t *list_sorted) {
     const uint32_t n = cell_start[g.ncells];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -294,8 +294,8 @@ k_count_neighbors(Counters *__restrict__ cnt, Grid g, const uint32_t *__restrict
 // ---- scatter from sorted order to original (rank) order for host-visible arrays -------------------------------
 template <typename T2>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_scatter_vec2(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
-               const uint32_t *__restrict__ rank_of_uid, const T2 *__restrict__ src, double2 *__restrict__ dst) {
+k_scatter_vec2(const uint32_t *n_ptr, const uint32_t *uid,
+               const uint32_t *rank_of_uid, const T2 *src, double2 *dst) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     const T2 v = src[s];
@@ -305,8 +305,8 @@ k_scatter_vec2(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ 
 }
 template <typename T>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_scatter_scalar(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
-                 const uint32_t *__restrict__ rank_of_uid, const T *__restrict__ src, double *__restrict__ dst) {
+k_scatter_scalar(const uint32_t *n_ptr, const uint32_t *uid,
+                 const uint32_t *rank_of_uid, const T *src, double *dst) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     dst[rank_of_uid[uid[s]]] = (double)src[s];
@@ -314,9 +314,9 @@ k_scatter_scalar(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict_
 // pressure / surface normal out of the packed PS records
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_scatter_ps(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
-             const uint32_t *__restrict__ rank_of_uid, const PS<Real> *__restrict__ src, double *__restrict__ prs,
-             double2 *__restrict__ tens) {
+k_scatter_ps(const uint32_t *n_ptr, const uint32_t *uid,
+             const uint32_t *rank_of_uid, const PS<Real> *src, double *prs,
+             double2 *tens) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     const PS<Real> v = src[s];
@@ -325,8 +325,8 @@ k_scatter_ps(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ ui
     if (tens) { double2 o; o.x = (double)v.sx; o.y = (double)v.sy; tens[r] = o; }
 }
 __global__ void __launch_bounds__(SC_BLOCK)
-k_scatter_uid(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
-              const uint32_t *__restrict__ rank_of_uid, uint32_t *__restrict__ dst) {
+k_scatter_uid(const uint32_t *n_ptr, const uint32_t *uid,
+              const uint32_t *rank_of_uid, uint32_t *dst) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     dst[rank_of_uid[uid[s]]] = uid[s];
@@ -334,9 +334,9 @@ k_scatter_uid(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ u
 
 // search taps: rows_sorted[s] = floor(y / d) of the particle at sorted index s, order[s] = its original index
 __global__ void __launch_bounds__(SC_BLOCK)
-k_tap_search(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__restrict__ pos,
-             const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
-             long long *__restrict__ rows_sorted, long long *__restrict__ order) {
+k_tap_search(const uint32_t *n_ptr, Grid g, const double2 *pos,
+             const uint32_t *uid, const uint32_t *rank_of_uid,
+             long long *rows_sorted, long long *order) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     rows_sorted[s] = (long long)floor(pos[s].y / g.d);
@@ -345,9 +345,9 @@ k_tap_search(const uint32_t *__restrict__ n_ptr, Grid g, const double2 *__restri
 
 // neighbor lists in original index order holding original indices, -1 padded (collision_detector.py:46-48)
 __global__ void __launch_bounds__(SC_BLOCK)
-k_tap_lists(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid,
-            const uint32_t *__restrict__ rank_of_uid, const uint32_t *__restrict__ count_by_rank,
-            const uint32_t *__restrict__ list_sorted, int *__restrict__ idx_out) {
+k_tap_lists(const uint32_t *n_ptr, const uint32_t *uid,
+            const uint32_t *rank_of_uid, const uint32_t *count_by_rank,
+            const uint32_t *list_sorted, int *idx_out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     const uint32_t r = rank_of_uid[uid[s]];
@@ -359,10 +359,10 @@ k_tap_lists(const uint32_t *__restrict__ n_ptr, const uint32_t *__restrict__ uid
 
 // wall contact counts V_i (crate.py:229-232) in original order
 __global__ void __launch_bounds__(SC_BLOCK)
-k_tap_wall_counts(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_constant__ WallParams W,
-                  const uint32_t *__restrict__ uid, const uint32_t *__restrict__ rank_of_uid,
-                  const uint32_t *__restrict__ wall_bits, const uint32_t *__restrict__ wall_slot,
-                  const double2 *__restrict__ wall_pre, int *__restrict__ out) {
+k_tap_wall_counts(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W,
+                  const uint32_t *uid, const uint32_t *rank_of_uid,
+                  const uint32_t *wall_bits, const uint32_t *wall_slot,
+                  const double2 *wall_pre, int *out) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
     int V = 0;
@@ -378,8 +378,8 @@ k_tap_wall_counts(const uint32_t *__restrict__ n_ptr, DevParams P, const __grid_
 
 // geometry_utils.py:7-39 as a dense P x S op (the reference's own unit test pins this one)
 __global__ void __launch_bounds__(SC_BLOCK)
-k_points_segments(const double2 *__restrict__ p, uint32_t P_, const double *__restrict__ seg, int S,
-                  double *__restrict__ nearest, double *__restrict__ dist) {
+k_points_segments(const double2 *p, uint32_t P_, const double *seg, int S,
+                  double *nearest, double *dist) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P_ * (uint32_t)S) return;
     const uint32_t i = t / (uint32_t)S, q = t % (uint32_t)S;
@@ -391,7 +391,7 @@ k_points_segments(const double2 *__restrict__ p, uint32_t P_, const double *__re
 
 // min / max cell coordinates of an arbitrary point set (standalone detect_particle_collisions)
 __global__ void __launch_bounds__(SC_BLOCK)
-k_cell_bounds(const double2 *__restrict__ pos, uint32_t n, double d, int *__restrict__ bounds /* rmin rmax cmin cmax */) {
+k_cell_bounds(const double2 *pos, uint32_t n, double d, int *bounds /* rmin rmax cmin cmax */) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double fr = floor(pos[i].y / d), fc = floor(pos[i].x / d);
@@ -409,14 +409,14 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
 // not touched the particle set in between), reset the per-tick counters, zero the cell histogram and both wall
 // bitmaps.  Entry [ncells] (the previous total) is deliberately not zeroed: the scan rewrites it.
 __global__ void __launch_bounds__(SC_BLOCK)
-k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, int carry_count,
-             uint32_t *__restrict__ bits_a, uint32_t *__restrict__ bits_b, uint32_t nbits_words,
-             unsigned long long *__restrict__ scan_desc, uint32_t scan_words) {
+k_begin_tick(Counters *cnt, uint32_t *cell_count, uint32_t ncells, int carry_count,
+             uint32_t *bits_a, uint32_t *bits_b, uint32_t nbits_words,
+             unsigned long long *scan_desc, uint32_t scan_words) {
     pdl_enter();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
-        cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0;
+        cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0; cnt->n_untiled = 0;
     }
     uint4 *c4 = reinterpret_cast<uint4 *>(cell_count);
     const uint32_t n4 = ncells / 4;
@@ -428,7 +428,7 @@ k_begin_tick(Counters *cnt, uint32_t *__restrict__ cell_count, uint32_t ncells, 
 
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_convert_vel_in(const double2 *__restrict__ src, typename Vec2<Real>::type *__restrict__ dst, uint32_t n) {
+k_convert_vel_in(const double2 *src, typename Vec2<Real>::type *dst, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     typename Vec2<Real>::type v;

@@ -56,7 +56,7 @@ struct TileWindows {
     bool staged, cells_staged;
 };
 
-__device__ __forceinline__ TileWindows tile_windows(const BlockDesc *__restrict__ desc) {
+__device__ __forceinline__ TileWindows tile_windows(const BlockDesc *desc) {
     const uint4 lo = reinterpret_cast<const uint4 *>(desc)[0], hi = reinterpret_cast<const uint4 *>(desc)[1];
     TileWindows w;
     w.base[0] = lo.x; w.base[1] = lo.y; w.base[2] = lo.z; w.c_lo = lo.w;
@@ -91,7 +91,7 @@ template <> __device__ __forceinline__ float2 SmemAcc<float2>::get(uint32_t L) c
     return v;
 }
 template <typename T> struct GmemAcc {
-    const T *__restrict__ p;
+    const T *p;
     __device__ __forceinline__ T get(uint32_t L) const { return p[L]; }
 };
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -119,9 +119,9 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 template <int kNoise, class Acc, class List>
 __device__ __forceinline__ void density_particle(const Acc &A, List lst, const TileWindows &w, bool live, uint32_t s,
                                                  const uint32_t (&b)[6], const Grid &g, const DevParams &P,
-                                                 Counters *__restrict__ cnt, const double2 *__restrict__ pos,
-                                                 uint2 *__restrict__ pair_rec, uint32_t *__restrict__ pair_off,
-                                                 uint8_t *__restrict__ pair_cnt, PS<float> *__restrict__ ps_out) {
+                                                 Counters *cnt, const double2 *pos,
+                                                 uint2 *pair_rec, uint32_t *pair_off,
+                                                 uint8_t *pair_cnt, PS<float> *ps_out) {
     const float df = (float)g.d;
     const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
     int K = 0;
@@ -220,11 +220,11 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
 
 template <int kNoise, int kRepeat = 1>
 __global__ void __launch_bounds__(SC_BLOCK, 6)
-k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *__restrict__ cell_start,
-               const BlockDesc *__restrict__ desc, const double2 *__restrict__ pos,
-               const SearchRec *__restrict__ rec, const uint32_t *__restrict__ cell_key,
-               uint2 *__restrict__ pair_rec, uint32_t *__restrict__ pair_off, uint8_t *__restrict__ pair_cnt,
-               PS<float> *__restrict__ ps_out) {
+k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
+               const BlockDesc *desc, const double2 *pos,
+               const SearchRec *rec, const uint32_t *cell_key,
+               uint2 *pair_rec, uint32_t *pair_off, uint8_t *pair_cnt,
+               PS<float> *ps_out) {
     pdl_enter();
     // staged: [records 20 KB | cell boundaries 5.25 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
     __shared__ __align__(16) unsigned char s_raw[SC_TILE_SMEM_K4];
@@ -273,6 +273,7 @@ k_density_tile(Counters *__restrict__ cnt, Grid g, DevParams P, const uint32_t *
                                              TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live, s, b, g, P, cnt, pos,
                                              pair_rec, pair_off, pair_cnt, ps_out);
     } else {
+        if (threadIdx.x == 0) atomicAdd(&cnt->n_untiled, 1u);  // rare; lets a test prove this path ran
         if (live) {
             const uint32_t *cs0 = cell_start + c - 1u;
             b[0] = cs0[0]; b[1] = cs0[3];

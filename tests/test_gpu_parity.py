@@ -215,6 +215,88 @@ def test_scene_mixed_per_step_tolerance(maker, n):
     assert np.abs(gp - ref["pos_out"]).max() <= REL_TOL_F32 * d
 
 
+def test_tiled_density_pass_through_blocks():
+    """The tiled density kernel's pass-through path (a block whose three windows do not fit the staging buffer: sparse
+    spray right above dense rows) really runs, and gives the per-step tolerance and the exact neighbor lists."""
+    import ctypes as C
+    from sand_crate_b200.scenes import _world
+    d = 1.0e-3
+    s = 0.75 * d
+    rs = np.random.RandomState(1)
+    # a shallow pool: 1200 particles per cell row, 40 rows
+    nx, ny = 1200, 40
+    xs = np.tile(0.05 + (np.arange(nx) + 0.5) * s, ny)
+    ys = np.repeat(1.0 - d - (np.arange(ny) + 0.5) * s, nx)
+    pool = np.stack((xs, ys), 1) + (rs.rand(nx * ny, 2) - 0.5) * 0.1 * s
+    # spray: one particle every other cell row above the pool
+    k = np.arange(400)
+    spray = np.stack((0.1 + 0.8 * rs.rand(len(k)), pool[:, 1].min() - d * (1.5 + 2 * k)), 1)
+    spray = spray[spray[:, 1] > 2 * d]
+    pos = np.concatenate((pool, spray))
+    vel = rs.randn(*pos.shape) * 0.05
+    world = _world(len(pos), d)
+    ctx, seg = _scene_ctx(world, pos, vel, _lib.PRECISION_MIXED, _lib.NOISE_COUNTER)
+    ctx.set_tick(0)
+    ctx.step()
+    L = _lib.load()
+    L.sc_debug_untiled_blocks.restype = C.c_int64
+    L.sc_debug_untiled_blocks.argtypes = [C.c_void_p]
+    assert L.sc_debug_untiled_blocks(ctx._h) > 0, "the scene must push at least one block onto the pass-through path"
+    gp, gv, _ = ctx.get_state()
+    cv = _coeff_vec(world.coefficients)
+    ref = O.step(cv, pos, vel.astype(np.float32).astype(np.float64), seg, [4], np.zeros((1, 5)), noise_mode=1,
+                 tkey=O.tick_key(0, 0), want_all=True)
+    assert np.abs(gv - ref["vel_out"]).max() <= REL_TOL_F32 * max(np.abs(ref["vel_out"]).max(), 1.0)
+    assert np.abs(gp - ref["pos_out"]).max() <= REL_TOL_F32 * d
+    counts, idx = ctx.get_neighbors(len(pos))
+    assert np.array_equal(counts, ref["nbr_count"]) and np.array_equal(idx, ref["nbr_idx_padded"])
+
+
+def test_free_run_is_reproducible():
+    """Two runs of the same scene give the same bits (regression: non-coherent loads under programmatic dependent
+    launch made fp64 free runs differ from run to run, see sc_common.cuh)."""
+    world, _ = world_from_freerun("wave_machine")
+    for precision in ("f64", "mixed"):
+        got = []
+        for _ in range(3):
+            np.random.seed(99)
+            crate = Crate(world, precision=precision, noise="counter")
+            for _ in range(150):
+                crate.physics_tick()
+            got.append((crate.particles.copy(), crate.particle_velocities.copy()))
+            crate.close()
+        for p, v in got[1:]:
+            assert np.array_equal(p, got[0][0]) and np.array_equal(v, got[0][1]), precision
+
+
+def test_mixed_mode_drift_stays_bounded_over_1000_ticks():
+    """North-star bar for the production mode: over 1000 ticks of wave_machine (sources, moving paddle, removal) the
+    mixed-precision run and the fp64 run - same counter noise - keep the same particle count and the same bulk state.
+    Individual trajectories decorrelate (the system is chaotic and noised), so the bound is on aggregates."""
+    world, _ = world_from_freerun("wave_machine")
+    runs = {}
+    for precision in ("f64", "mixed"):
+        np.random.seed(1234)   # the sources draw from the global stream (particle_source.py)
+        crate = Crate(world, precision=precision, noise="counter")
+        for _ in range(1000):
+            crate.physics_tick()
+        runs[precision] = (crate.particle_count, crate.particles.copy(), crate.particle_velocities.copy(),
+                           crate.particles_pressure.copy())
+        crate.close()
+    (n64, p64, v64, q64), (n32, p32, v32, q32) = runs["f64"], runs["mixed"]
+    r = world.coefficients["particle_radius"]
+    assert abs(n64 - n32) <= 0.01 * n64 and n64 > 1500   # removal at the rim may differ by a few particles
+    m = min(n64, n32)
+    assert np.isfinite(p32).all() and np.isfinite(v32).all() and p32.min() >= -r and p32.max() <= 1 + r
+    assert np.abs(p64.mean(0) - p32.mean(0)).max() < 0.02            # centre of mass: within 2 % of the box
+    assert abs(np.sqrt((v64 ** 2).sum(1)).mean() - np.sqrt((v32 ** 2).sum(1)).mean()) < 0.15 * max(
+        np.sqrt((v64 ** 2).sum(1)).mean(), 0.05)                    # mean speed
+    assert abs(q64.mean() - q32.mean()) < 0.15 * max(q64.mean(), 0.1)  # mean pressure
+    hist64 = np.histogram(p64[:, 1], bins=10, range=(0, 1))[0]
+    hist32 = np.histogram(p32[:, 1], bins=10, range=(0, 1))[0]
+    assert np.abs(hist64 - hist32).max() < 0.05 * m                  # vertical density profile
+
+
 # ---- size-independent properties at the benchmark size ----------------------------------------------------------
 def test_dam_break_1m_properties():
     n = 1_000_000
