@@ -123,13 +123,12 @@ static cudaError_t launch_maybe_pdl(bool pdl, void (*kernel)(KArgs...), dim3 gri
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-// Which of the strip-exchange kernels (1 pack, 2 push, 4 unpack) are launched with programmatic stream serialization.
-// Default none: with push AND unpack both launched that way an interior rank (two neighbors, direct NVLink transport)
-// hit an illegal address on 4xB200, cause not understood; every other combination passed the bit-parity check, but
-// the few microseconds are not worth an unexplained hazard.  SC_DIST_PDL overrides (developer switch).
+// Which of the strip-exchange kernels (1 pack, 2 push, 4 unpack) are launched with programmatic stream serialization:
+// all of them.  SC_DIST_PDL overrides (developer switch, kept from the hunt for the stale-read hazard described in
+// sc_common.cuh: before that fix, push + unpack launched this way faulted on interior ranks).
 static int dist_pdl_mask() {
     static int m = -1;
-    if (m < 0) { const char *e = getenv("SC_DIST_PDL"); m = e ? atoi(e) : 0; }
+    if (m < 0) { const char *e = getenv("SC_DIST_PDL"); m = e ? atoi(e) : 7; }
     return m;
 }
 

@@ -98,7 +98,9 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
 // exclusive scan of a u32 array, in place, total written to a[n] (three launches: reduce, scan sums, apply).
 // 16 items per thread as four 128-bit accesses: a warp request covers 2 KB contiguous.
 #define SC_SCAN_ITEMS 16
-// few, large tiles (256- and 512-thread tiles measured 2-4 us slower on the 1.8M-cell grid)
+// few, large tiles (256- and 512-thread tiles measured 2-4 us slower on the 1.8M-cell grid; a row-wise scan without
+// any look-back - one block per cell row, row totals accumulated by the pre-pass - measured 6 us slower in the scan
+// and 6 us slower in the pre-pass)
 #ifndef SC_SCAN_THREADS
 #define SC_SCAN_THREADS 1024
 #endif
