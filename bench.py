@@ -407,7 +407,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": SURVEY_BYTES[top], "kernel_ms": k_ms,
-                         "note": "K4 is issue-bound, not HBM-bound (ncu: 61 % issue-active, 7 % DRAM; profiles/)",
+                         "note": "K4 is issue-bound, not HBM-bound (ncu: 74 % issue-active at 22 of 32 lanes, 6 % DRAM; profiles/r1u_ncu_full_summary.csv)",
                          "design": {"bytes_per_particle": ALGO_BYTES[top], "achieved": design_achieved,
                                     "frac": design_achieved / peak, "mean_pairs_per_particle": mean_pairs},
                          "whole_step": {"survey_bytes_per_particle": 178,
