@@ -80,8 +80,12 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=open(self.path, "w"),
                                          stderr=subprocess.DEVNULL)
+            # nvidia-smi takes a few hundred ms to come up and the timed region is short: wait for its first line
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 5.0 and os.path.getsize(self.path) == 0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -109,6 +113,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
+            sm = sm[1:] if len(sm) > 2 else sm   # the first line predates the load
             out["sm_mhz"] = float(np.median(sm))
             out["samples"] = len(sm)
         out["reasons"] = sorted(reasons)
