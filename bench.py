@@ -341,8 +341,8 @@ def main():
         def e2e_step():
             crate.set_particles(hp, hv)
             crate.physics_tick()
-            return crate._ctx.get_state(want_vel=False, want_pressure=False)[0]
-        e2e_api = "Crate.set_particles(host) -> physics_tick() -> particles (host)"
+            return crate.particles
+        e2e_api = "Crate.set_particles(host, page-locked) -> physics_tick() -> Crate.particles (host, page-locked)"
     else:
         uid0, gp, gv = dom.owned()
         m = len(uid0)
@@ -353,8 +353,9 @@ def main():
         def e2e_step():
             dom.ctx.set_state_uids(hp, hv, uid0)
             dom.physics_tick()
-            return dom.ctx.dist_get_owned()[0]
-        e2e_api = "Context.set_state_uids(host) -> StripDomain.physics_tick() -> dist_get_owned (host), per rank"
+            return dom.ctx.dist_get_owned(want_vel=False, want_uid=False, reuse=True)[0]
+        e2e_api = ("Context.set_state_uids(host, page-locked) -> StripDomain.physics_tick() -> "
+                   "dist_get_owned (positions, host, page-locked), per rank")
     for _ in range(3):
         out_pos = e2e_step()
     barrier()

@@ -83,6 +83,13 @@ int sc_particle_count(sc_ctx *ctx, int64_t *n);                     /* crate.py:
 int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *pressure, int64_t cap, int64_t *n);
 int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n);
 
+/* Page-locked host memory for the buffers handed to sc_set_state / sc_append_particles / sc_get_state /
+ * sc_dist_get_owned.  No reference counterpart (the reference never leaves the host); with pageable buffers the
+ * copies are staged by the driver and run at a fraction of the PCIe rate.  The host mirror keeps its readback arrays
+ * (crate.py:24-26 `particles`, `particle_velocities`, `particles_pressure`) in such memory. */
+int sc_host_alloc(size_t bytes, void **out);
+int sc_host_free(void *p);
+
 /* ---- the step ------------------------------------------------------------------------------------------ */
 /* One tick = remove_particles (crate.py:149-159) -> calc_virtual_colliders + apply_hard_wall_fix (213-243,
  * 202-211) -> detect_particle_collisions (collision_detector.py:9-49) -> populate_colliders (161-175) ->

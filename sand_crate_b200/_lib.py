@@ -47,6 +47,8 @@ SIGNATURES = {
     "sc_destroy": (None, [_ctx]),
     "sc_last_error": (C.c_char_p, [_ctx]),
     "sc_version": (C.c_int, []),
+    "sc_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "sc_host_free": (C.c_int, [C.c_void_p]),
     "sc_set_params": (C.c_int, [_ctx, C.POINTER(ScParams)]),
     "sc_set_walls": (C.c_int, [_ctx, _dp, C.c_int, _ip, _dp, C.c_int]),
     "sc_set_noise": (C.c_int, [_ctx, C.c_int, C.c_uint64]),
@@ -123,6 +125,33 @@ def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else None
 
 
+class PinnedArray:
+    """A NumPy array over page-locked host memory (sc_host_alloc); freed when this object is closed or collected."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._L = load()
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = C.c_void_p()
+        if self._L.sc_host_alloc(max(nbytes, 1), C.byref(self._p)):
+            raise SandCrateError(self._L.sc_last_error(None).decode())
+        raw = (C.c_byte * max(nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            self._L.sc_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """Owns one `sc_ctx`.  Thin: every method is one C-ABI call plus NumPy buffer management."""
 
@@ -141,6 +170,19 @@ class Context:
         if getattr(self, "_h", None) is not None and self._h.value is not None:
             self._L.sc_destroy(self._h)
             self._h = _ctx()
+        for b in getattr(self, "_pinned", {}).values():
+            b.close()
+        self._pinned = {}
+
+    def _pinned_rows(self, name: str, rows: int, shape_tail=(), dtype=np.float64):
+        """A reusable page-locked readback buffer with room for `rows` rows (grown by doubling)."""
+        bufs = self.__dict__.setdefault("_pinned", {})
+        b = bufs.get(name)
+        if b is None or b.shape[0] < rows:
+            if b is not None:
+                b.close()
+            b = bufs[name] = PinnedArray((max(rows, self.capacity),) + tuple(shape_tail), dtype)
+        return b.array
 
     def __del__(self):
         try:
@@ -185,11 +227,21 @@ class Context:
         self._ck(self._L.sc_particle_count(self._h, C.byref(n)))
         return n.value
 
-    def get_state(self, want_vel=True, want_pressure=True):
+    def get_state(self, want_vel=True, want_pressure=True, reuse=False, want_pos=True):
+        """reuse=True: the arrays are views of this context's page-locked readback buffers - valid until the next
+        reuse=True call or close() (the reference's own `particles` array is updated in place just the same)."""
         n = self.particle_count()
-        pos = np.empty((n, 2))
-        vel = np.empty((n, 2)) if want_vel else None
-        prs = np.empty(n) if want_pressure else None
+        if not want_pos:
+            pos = None
+        elif reuse:
+            pos = self._pinned_rows("pos", n, (2,))[:n]
+        if reuse:
+            vel = self._pinned_rows("vel", n, (2,))[:n] if want_vel else None
+            prs = self._pinned_rows("prs", n)[:n] if want_pressure else None
+        else:
+            pos = np.empty((n, 2)) if want_pos else None
+            vel = np.empty((n, 2)) if want_vel else None
+            prs = np.empty(n) if want_pressure else None
         m = C.c_int64()
         self._ck(self._L.sc_get_state(self._h, _ptr(pos, _dp), _ptr(vel, _dp), _ptr(prs, _dp), n, C.byref(m)))
         assert m.value == n
@@ -308,12 +360,24 @@ class Context:
     def dist_set_rows(self, row_lo: int, row_hi: int):
         self._ck(self._L.sc_dist_set_rows(self._h, int(row_lo), int(row_hi)))
 
-    def dist_get_owned(self):
+    def dist_get_owned(self, want_vel=True, want_uid=True, reuse=False):
+        """(pos, vel, uid) of the owned particles.  reuse=True: views of page-locked buffers, valid until the next
+        reuse=True call; parts not asked for come back as None."""
         cap = self.capacity
-        pos, vel, uid = np.empty((cap, 2)), np.empty((cap, 2)), np.empty(cap, np.uint32)
         n = C.c_int64()
+        if reuse:
+            pos = self._pinned_rows("own_pos", cap, (2,))
+            vel = self._pinned_rows("own_vel", cap, (2,)) if want_vel else None
+            uid = self._pinned_rows("own_uid", cap, (), np.uint32) if want_uid else None
+        else:
+            pos = np.empty((cap, 2))
+            vel = np.empty((cap, 2)) if want_vel else None
+            uid = np.empty(cap, np.uint32) if want_uid else None
         self._ck(self._L.sc_dist_get_owned(self._h, _ptr(pos, _dp), _ptr(vel, _dp), _ptr(uid, _up), cap, C.byref(n)))
-        return pos[:n.value].copy(), vel[:n.value].copy(), uid[:n.value].copy()
+        m = n.value
+        if reuse:
+            return pos[:m], None if vel is None else vel[:m], None if uid is None else uid[:m]
+        return pos[:m].copy(), None if vel is None else vel[:m].copy(), None if uid is None else uid[:m].copy()
 
     def dist_status(self, send_lo=None, send_hi=None):
         ov, far, n = C.c_int(), C.c_int(), C.c_int64()

@@ -125,7 +125,8 @@ class Crate:
     def _ensure_capacity(self, needed: int) -> None:
         if needed <= self._ctx.capacity:
             return
-        pos, vel, _ = self._ctx.get_state(want_pressure=False)
+        pos, vel, _ = self._ctx.get_state(want_pressure=False)   # own arrays: they must outlive the old context
+        self._cache = {}
         self._ctx.close()
         self._open_context(max(needed, 2 * self._ctx.capacity))
         self._push_params()
@@ -135,6 +136,7 @@ class Crate:
 
     def close(self) -> None:
         if self._ctx is not None:
+            self._cache = {}
             self._ctx.close()
             self._ctx = None
 
@@ -158,23 +160,26 @@ class Crate:
             self._count = self._ctx.particle_count()
         return self._count
 
-    def _fetch(self) -> dict:
-        if not self._cache:
-            pos, vel, prs = self._ctx.get_state()
-            self._cache = {"pos": pos, "vel": vel, "prs": prs}
-        return self._cache
+    def _fetch(self, key: str) -> np.ndarray:
+        """One device -> host read per attribute per tick, into page-locked buffers that are refilled in place: like
+        the reference's arrays, what `particles` returned last tick is overwritten by this tick's read."""
+        if key not in self._cache:
+            pos, vel, prs = self._ctx.get_state(want_pos=key == "pos", want_vel=key == "vel",
+                                                want_pressure=key == "prs", reuse=True)
+            self._cache[key] = {"pos": pos, "vel": vel, "prs": prs}[key]
+        return self._cache[key]
 
     @property
     def particles(self) -> np.ndarray:
-        return self._fetch()["pos"]
+        return self._fetch("pos")
 
     @property
     def particle_velocities(self) -> np.ndarray:
-        return self._fetch()["vel"]
+        return self._fetch("vel")
 
     @property
     def particles_pressure(self) -> np.ndarray:
-        return self._fetch()["prs"]
+        return self._fetch("prs")
 
     def set_particles(self, particles, velocities=None) -> None:
         """Replaces the whole particle set (rows get indices 0..n-1).  Not in the reference (it only grows through

@@ -520,6 +520,20 @@ extern "C" int sc_append_particles(sc_ctx *ctx, const double *pos, const double 
     return upload_particles(ctx, pos, vel, ctx->n_host, n);
 }
 
+extern "C" int sc_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(nullptr, "sc_host_alloc: out is NULL");
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(nullptr, std::string("sc_host_alloc: ") + cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int sc_host_free(void *p) {
+    if (!p) return 0;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail(nullptr, std::string("sc_host_free: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int sc_particle_count(sc_ctx *ctx, int64_t *n) {
     if (!ctx || !n) return fail(ctx, "sc_particle_count: NULL argument");
     CK(cudaSetDevice(ctx->device));

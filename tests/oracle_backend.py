@@ -66,7 +66,7 @@ class OracleContext:
     def particle_count(self):
         return len(self.pos)
 
-    def get_state(self, want_vel=True, want_pressure=True):
+    def get_state(self, want_vel=True, want_pressure=True, reuse=False, want_pos=True):
         return self.pos.copy(), self.vel.copy(), self.prs.copy()
 
     def _coeffs(self):
@@ -181,7 +181,7 @@ class OracleContext:
     def dist_set_rows(self, row_lo, row_hi):
         self.dist["lo"], self.dist["hi"] = row_lo, row_hi
 
-    def dist_get_owned(self):
+    def dist_get_owned(self, want_vel=True, want_uid=True, reuse=False):
         own = (self.uid & self.GHOST) == 0
         return self.pos[own].copy(), self.vel[own].copy(), self.uid[own].copy()
 
