@@ -11,7 +11,7 @@ ctx.set_noise(_lib.NOISE_COUNTER, 0); ctx.set_state(pos, vel); ctx.step(300); ct
 L = _lib.load(); L.sc_debug_rerun.restype = C.c_double; L.sc_debug_rerun.argtypes = [C.c_void_p, C.c_int, C.c_int]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 import os
-for which in ((4, 24, 5, 25) if os.environ.get('SC_RERUN_REPEAT') else (4, 5)):
+for which in ((4, 24, 5) if os.environ.get('SC_RERUN_REPEAT') else (4, 5)):
     warm = L.sc_debug_rerun(ctx._h, which, 20)
     cold = []
     for _ in range(10):

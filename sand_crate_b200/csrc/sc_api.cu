@@ -222,6 +222,7 @@ static void refresh_wall_boxes(sc_ctx *ctx);
 static int sync_count(sc_ctx *ctx);
 
 #define SC_DIST_ROW_SLACK 96
+#define SC_K5_THREADS 128  // K5 block size: 128 measured 2 us faster than 256 (blocks drain sooner, the gather-latency-bound kernel keeps more warps resident)
 
 // Cell grid of the world box; in strip mode only the rows this rank can ever hold (its strip, the halo, and the
 // one-row shift the wall fix can add), so clearing and scanning the grid scales with the strip, not the scene.
@@ -680,8 +681,11 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
     typedef typename Vec2<Real>::type R2;
     if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
     ProfScope ps(ctx, SLOT_FORCE);
+    static int k5_threads = 0;  // SC_K5_THREADS: developer switch for A/B timing of the block size
+    if (!k5_threads) { const char *e = getenv("SC_K5_THREADS"); k5_threads = e ? atoi(e) : SC_K5_THREADS; }
+    const unsigned nt = (unsigned)k5_threads, nb = (unsigned)((n + nt - 1) / nt);
     auto go = [&](auto kernel) {
-        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
+        return launch_pdl(kernel, dim3(nb), dim3(nt), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
                           (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
                           (const PS<Real> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre,
                           ctx->pos_cur, (R2 *)ctx->vel_cur, ctx->monitor);
@@ -1053,14 +1057,7 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
         if (which == 4 || which == 24) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
         cudaEventRecord(e0, ctx->stream);
         const bool tiled = ctx->pair_mode != 0 && dp.noise_mode != SC_NOISE_HOST;
-        if (which == 25) {
-            typedef float2 R2;
-            launch_pdl(k_force<float, false, true>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                       (const uint32_t *)(ctx->cell_start + ctx->grid.ncells), dp, ctx->walls, ctx->pos_srt,
-                       (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
-                       (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, ctx->pos_cur,
-                       (R2 *)ctx->vel_cur, ctx->monitor);
-        } else if (which == 24) {
+        if (which == 24) {
             launch_pdl(k_density_tile<SC_NOISE_COUNTER, 2>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt,
                        ctx->grid, dp, ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt,
                        (uint2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);

@@ -310,7 +310,7 @@ k_density(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
 
 // Everything of K5 that follows the pair loop, for particle s: wall contact rows of F5, F3-F6 velocity updates, wall
 // bounce, continuous collision, integration.  `visc(vx, vy, ax, ay)` supplies sum_j (v_j - v) (crate.py:319-323).
-template <typename Real, bool kMonitor, bool kNoRare = false, typename ViscFn>
+template <typename Real, bool kMonitor, typename ViscFn>
 __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx, Real ty, Real qx, Real qy,
                                            const DevParams &P, const WallParams &W, const double2 *pos,
                                            const typename Vec2<Real>::type *vel,
@@ -335,7 +335,7 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
     int V = 0;
     double wnx = 0, wny = 0, wux = 0, wuy = 0;  // sequential sums for np.mean (crate.py:249-250)
     const bool touching = (wall_bits[s >> 5] >> (s & 31)) & 1u;
-    if (!kNoRare && touching) {
+    if (touching) {
         const double2 pre = wall_pre[wall_slot[s]];
         int nb[SC_MAX_BODIES];
         for (int b = 0; b < W.nbodies; ++b) nb[b] = 0;
@@ -412,7 +412,7 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
         const double mxlo = fmin(ps.x, bx), mxhi = fmax(ps.x, bx), mylo = fmin(ps.y, by), myhi = fmax(ps.y, by);
         // one test for the bulk of the liquid: the movement stays inside a rectangle no padded segment reaches
         const bool clear = mxlo > W.safe_ccd[0] && mxhi < W.safe_ccd[1] && mylo > W.safe_ccd[2] && myhi < W.safe_ccd[3];
-        if (!kNoRare && !clear) {
+        if (!clear) {
             const double bax = bx - ps.x, bay = by - ps.y;
             for (int q = 0; q < 2 * W.S; ++q) {
                 if (mxhi < W.pad_box[q][0] || mxlo > W.pad_box[q][1] || myhi < W.pad_box[q][2] || mylo > W.pad_box[q][3])
@@ -455,7 +455,7 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
 #ifndef SC_K5_MINBLOCKS
 #define SC_K5_MINBLOCKS 1
 #endif
-template <typename Real, bool kMonitor, bool kNoRare = false>  // kNoRare: developer timing aid (wrong results)
+template <typename Real, bool kMonitor>
 __global__ void __launch_bounds__(SC_BLOCK, SC_K5_MINBLOCKS)
 k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W,
         const double2 *pos, const typename Vec2<Real>::type *vel,
@@ -513,7 +513,7 @@ k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W
             }
     }
 
-    force_tail<Real, kMonitor, kNoRare>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
+    force_tail<Real, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
                                monitor, n_ptr, [&](Real vx, Real vy, Real &ax, Real &ay) {
         if constexpr (sizeof(Real) == 8) {
             for (int q = 0; q < K; ++q) {
