@@ -269,6 +269,27 @@ def test_free_run_is_reproducible():
             assert np.array_equal(p, got[0][0]) and np.array_equal(v, got[0][1]), precision
 
 
+def test_crate_readback_is_page_locked_and_refilled_in_place():
+    """`Crate.particles` and friends are read once per attribute per tick into page-locked buffers that are refilled in
+    place (like the reference, whose arrays are updated in place); `Context.get_state()` keeps handing out fresh arrays."""
+    world, _ = world_from_freerun("wave_machine")
+    np.random.seed(3)
+    crate = Crate(world, precision="mixed", noise="counter")
+    for _ in range(20):
+        crate.physics_tick()
+    p1 = crate.particles
+    assert crate.particles is p1                      # cached within the tick
+    keep = p1.copy()
+    fresh, _, _ = crate._ctx.get_state(want_vel=False, want_pressure=False)
+    assert np.array_equal(fresh, keep) and not np.shares_memory(fresh, p1)
+    crate.physics_tick()
+    p2 = crate.particles
+    assert np.shares_memory(p1[:1], p2[:1]) or len(p2) != len(p1)   # same buffer again
+    assert not np.array_equal(p2[:len(keep)], keep[:len(p2)])        # and it now holds the new tick
+    assert len(crate.particle_velocities) == len(p2) == len(crate.particles_pressure)
+    crate.close()
+
+
 def test_mixed_mode_drift_stays_bounded_over_1000_ticks():
     """North-star bar for the production mode: over 1000 ticks of wave_machine (sources, moving paddle, removal) the
     mixed-precision run and the fp64 run - same counter noise - keep the same particle count and the same bulk state.
