@@ -42,7 +42,7 @@ struct sc_ctx {
     double2 *pos_cur = nullptr, *pos_srt = nullptr;
     float2 *rel_srt = nullptr;        // cell-relative fp32 positions of the sorted set
     float4 *rec_srt = nullptr;        // mixed mode: (rel, cell column, uid) search records of the tiled pair kernels
-    BlockDesc *blk_desc = nullptr;    // mixed mode: per block of SC_BLOCK sorted particles, its three windows
+    BlockDesc *blk_desc = nullptr;    // mixed mode: per block of SC_TILE sorted particles, its three windows
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
     uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
@@ -293,7 +293,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, &c->rel_srt, n);
     if (precision == SC_PRECISION_MIXED) {
         rc |= dev_alloc(c, &c->rec_srt, n);
-        rc |= dev_alloc(c, &c->blk_desc, (n + SC_BLOCK - 1) / SC_BLOCK + 1);
+        rc |= dev_alloc(c, &c->blk_desc, (n + SC_TILE - 1) / SC_TILE + 1);
     }
     rc |= dev_alloc(c, (char **)&c->ps, n * 4 * rs);
     rc |= dev_alloc(c, &c->pair_j, n * SC_MAX_NEIGHBORS);
@@ -697,8 +697,8 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
 // mixed precision with device-side noise: K4 stages the block's neighborhood in shared memory (sc_tile.cuh)
 static int launch_density_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
     auto go = [&](auto kernel) {
-        return launch_pdl(kernel, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt, g, dp, ctx->cell_start,
-                          ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt, (uint2 *)ctx->pair_n,
+        return launch_pdl(kernel, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, ctx->cnt, g, dp,
+                          ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt, (uint2 *)ctx->pair_n,
                           ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
     };
     CK(dp.noise_mode == SC_NOISE_COUNTER ? go(k_density_tile<SC_NOISE_COUNTER>) : go(k_density_tile<SC_NOISE_NONE>));
@@ -1058,7 +1058,7 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
         cudaEventRecord(e0, ctx->stream);
         const bool tiled = ctx->pair_mode != 0 && dp.noise_mode != SC_NOISE_HOST;
         if (which == 24) {
-            launch_pdl(k_density_tile<SC_NOISE_COUNTER, 2>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream, ctx->cnt,
+            launch_pdl(k_density_tile<SC_NOISE_COUNTER, 2>, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, ctx->cnt,
                        ctx->grid, dp, ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt,
                        (uint2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
         } else if (which == 4) { if (tiled) launch_density_tile(ctx, ctx->grid, dp, n); else launch_density<float>(ctx, ctx->grid, dp, nullptr, n); }

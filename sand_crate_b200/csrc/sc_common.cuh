@@ -15,6 +15,10 @@
 
 #define SC_INVALID_CELL 0xFFFFFFFFu
 #define SC_BLOCK 256
+// particles per block of the tiled density kernel (sc_tile.cuh) = granularity of the window descriptors
+#ifndef SC_TILE
+#define SC_TILE 256
+#endif
 
 namespace sc {
 

@@ -249,11 +249,11 @@ k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
     }
     if (desc) {  // the block of the tiled pair kernels this particle opens / closes: its three windows (sc_tile.cuh)
         const uint32_t nc = (uint32_t)g.ncols;
-        if ((f & (SC_BLOCK - 1u)) == 0u)
-            reinterpret_cast<uint4 *>(desc + f / SC_BLOCK)[0] =
+        if ((f & (SC_TILE - 1u)) == 0u)
+            reinterpret_cast<uint4 *>(desc + f / SC_TILE)[0] =
                 make_uint4(cell_start[c - 1u], cell_start[c + nc - 1u], cell_start[c - nc - 1u], c);
-        if ((f & (SC_BLOCK - 1u)) == SC_BLOCK - 1u || f == n - 1u)
-            reinterpret_cast<uint4 *>(desc + f / SC_BLOCK)[1] =
+        if ((f & (SC_TILE - 1u)) == SC_TILE - 1u || f == n - 1u)
+            reinterpret_cast<uint4 *>(desc + f / SC_TILE)[1] =
                 make_uint4(cell_start[c + 2u], cell_start[c + nc + 2u], cell_start[c - nc + 2u], c);
     }
     vel_s[f] = vel[i];

@@ -1,7 +1,7 @@
 // sc_tile.cuh - the production (mixed precision, device noise) density kernel: K4 with the neighborhood of a block
 // staged in shared memory.
 //
-// A block owns SC_BLOCK consecutive particles of the sorted set.  Because the sort is cell-major (row, col, x), every
+// A block owns SC_TILE consecutive particles of the sorted set.  Because the sort is cell-major (row, col, x), every
 // neighbor of those particles lies in one of three CONTIGUOUS windows of the sorted set - the block's own stretch of
 // its cell row(s) widened by one cell at each end, and the same stretch of cells one row below / one row above:
 //
@@ -31,8 +31,9 @@
 
 namespace sc {
 
-#define SC_TILE_CAP 1280    // staged particles per block (3 windows of ~SC_BLOCK + a few cells each)
-#define SC_TILE_CELLS 448   // staged cell boundaries per row (blocks that wrap around a row end read them from global)
+#define SC_TILE_CAP (5 * SC_TILE)              // staged particles per block (3 windows of ~SC_TILE + a few cells each)
+#define SC_TILE_CELLS (SC_TILE + SC_TILE / 2 + 64)  // staged cell boundaries per row (blocks that wrap around a row end
+                                               // read them from global)
 
 // search record of one sorted particle, written by k_rank_gather in mixed mode:
 //   x, y = cell-relative position (see collect_neighbors), z = (float)cell column, w = uid bits
@@ -40,7 +41,7 @@ namespace sc {
 //   x_j - x_i = (rel_j.x - rel_i.x) + (col_j - col_i) * d     with col_j - col_i in {-1, 0, 1}, exact in fp32.
 typedef float4 SearchRec;
 
-// Per block of SC_BLOCK sorted particles, written by k_rank_gather (the threads that place the block's first and last
+// Per block of SC_TILE sorted particles, written by k_rank_gather (the threads that place the block's first and last
 // particle): the three windows and the block's first / last cell.  One 32-byte read replaces a chain of dependent
 // loads (particle count -> cell keys -> cell boundaries) at the head of K4 and K5.
 struct __align__(16) BlockDesc {
@@ -99,9 +100,9 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)
 // per-thread neighbor list, one column per thread; 16-bit entries when the indices are local (11 bits + row code)
 template <typename E, int kShift> struct TileList {
     E *col;
-    __device__ __forceinline__ void set(int k, uint32_t L, uint32_t code) { col[k * SC_BLOCK] = (E)(L | (code << kShift)); }
+    __device__ __forceinline__ void set(int k, uint32_t L, uint32_t code) { col[k * SC_TILE] = (E)(L | (code << kShift)); }
     __device__ __forceinline__ void get(int k, uint32_t &L, uint32_t &code) const {
-        const uint32_t e = col[k * SC_BLOCK];
+        const uint32_t e = col[k * SC_TILE];
         L = e & ((1u << kShift) - 1u); code = e >> kShift;
     }
 };
@@ -216,10 +217,10 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
     ps_out[s] = o;
 }
 
-#define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_BLOCK * 2)
+#define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_TILE * 2)
 
 template <int kNoise, int kRepeat = 1>
-__global__ void __launch_bounds__(SC_BLOCK, 6)
+__global__ void __launch_bounds__(SC_TILE, 1536 / SC_TILE)
 k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
                const BlockDesc *desc, const double2 *pos,
                const SearchRec *rec, const uint32_t *cell_key,
@@ -228,8 +229,8 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
     pdl_enter();
     // staged: [records 20 KB | cell boundaries 5.25 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
     __shared__ __align__(16) unsigned char s_raw[SC_TILE_SMEM_K4];
-    static_assert(SC_TILE_SMEM_K4 >= SC_MAX_NEIGHBORS * SC_BLOCK * 4, "pass-through lists must fit");
-    const uint32_t b0 = blockIdx.x * SC_BLOCK;
+    static_assert(SC_TILE_SMEM_K4 >= SC_MAX_NEIGHBORS * SC_TILE * 4, "pass-through lists must fit");
+    const uint32_t b0 = blockIdx.x * SC_TILE;
     const uint32_t s = b0 + threadIdx.x;
     // first round of loads, all independent: live count, block descriptor, own cell
     const uint32_t n = cell_start[g.ncells];
@@ -245,11 +246,11 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
         uint16_t *s_list = reinterpret_cast<uint16_t *>(s_raw + SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4);
         // second round: the three windows and (unless the block wraps around a row end) its cell boundaries, stored
         // as local indices
-        for (uint32_t t = threadIdx.x; t < w.total; t += SC_BLOCK) s_rec[t] = rec[tile_source(w, t)];
+        for (uint32_t t = threadIdx.x; t < w.total; t += SC_TILE) s_rec[t] = rec[tile_source(w, t)];
         const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
         if (w.cells_staged) {
             const uint32_t *src = cell_start + w.c_lo - 1u;
-            for (uint32_t t = threadIdx.x; t < w.ncw; t += SC_BLOCK) {
+            for (uint32_t t = threadIdx.x; t < w.ncw; t += SC_TILE) {
                 s_cs[t] = src[t] + d0;
                 s_cs[SC_TILE_CELLS + t] = src[nc + t] + d1;
                 s_cs[2 * SC_TILE_CELLS + t] = (src - nc)[t] + d2;
