@@ -220,7 +220,10 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
 #define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_TILE * 2)
 
 template <int kNoise, int kRepeat = 1>
-__global__ void __launch_bounds__(SC_TILE, 1536 / SC_TILE)
+#ifndef SC_TILE_RESIDENT
+#define SC_TILE_RESIDENT 1536  // threads per SM the register allocation is held to (1536 = 40 registers)
+#endif
+__global__ void __launch_bounds__(SC_TILE, SC_TILE_RESIDENT / SC_TILE)
 k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
                const BlockDesc *desc, const double2 *pos,
                const SearchRec *rec, const uint32_t *cell_key,
