@@ -52,13 +52,19 @@ def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
         world, pos, vel = (box_fill if scene == "box_fill" else dam_break)(n)
+        cuts = None
         if scene == "dam_break_shifted":   # start from a partition that is wrong for the scene: cuts must move
             pos = pos.copy()
             pos[:, 1] -= 0.1
+        if scene == "dam_break_wrong_cuts":  # the equal-count cuts of ANOTHER scene (tests/mgpu_check.py, case 3)
+            from sand_crate_b200.strips import partition_rows, rows_of
+            shifted = pos.copy()
+            shifted[:, 1] -= 0.1
+            cuts = partition_rows(rows_of(shifted, 2 * world.coefficients["particle_radius"]), world_size)
         vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0  # fast particles: migration every tick
         dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision="f64", noise="counter",
                           noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"),
-                          rebalance_every=rebalance_every)
+                          rebalance_every=rebalance_every, cuts=cuts)
         cuts0 = list(dom.cuts)
         migrated = 0
         for _ in range(ticks):
@@ -128,3 +134,27 @@ def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
     assert not stats[:, 1].any()
     owned = stats[:, 4]
     assert owned.max() - owned.min() < 0.25 * n / world_size, owned
+
+
+def test_sliding_cuts_four_ranks_two_interior(tmp_path):
+    """Four strips (two interior ranks with two moving cuts each) started from the cuts of another scene and re-cut
+    every 3 ticks: still bit-identical to the single-domain run (the case tests/mgpu_check.py runs on 4 GPUs)."""
+    n, ticks, world_size = 8000, 10, 4
+    mp.spawn(_worker, args=(world_size, _free_port(), "dam_break_wrong_cuts", n, ticks, str(tmp_path), 3),
+             nprocs=world_size, join=True)
+    got = np.load(tmp_path / "out.npz")
+    stats = np.load(tmp_path / "stats.npy")
+    world, pos, vel = dam_break(n)
+    vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = _coeff_vec(world.coefficients)
+    uid = np.arange(n, dtype=np.uint32)
+    for tick in range(ticks):
+        pos, vel, mask = O.remove_particles(pos, vel, world.coefficients["particle_radius"])
+        uid = uid[~mask]
+        out = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(11, tick), uid=uid,
+                     want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+    assert np.array_equal(got["uid"], uid) and np.array_equal(got["pos"], pos) and np.array_equal(got["vel"], vel)
+    assert stats[:, 3].all(), "the cuts must have moved"
+    assert not stats[:, 1].any()
