@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py - particle-steps/sec of the SandCrate step on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--scene dam_break|box_fill]
-    python bench.py --impl reference ...        # the CPU port of the reference step on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--scene dam_break|box_fill|dam_break_wide]
+    python bench.py --impl reference ...        # the reference's CPU step on the host cores (same scene mapping)
 
-One "step" = one `physics_tick` over the whole synthetic scene.  N = 1: dam-break, 1M particles (BASELINE.json
-configs[2]).  Timed with CUDA events on the stream the kernels are launched on; L2 is flushed between timed steps
-(the 1M scene's working set is smaller than the 126 MB L2).  Prints ONE JSON line.
+One "step" = one `physics_tick` over the whole synthetic scene.
+  N = 1: dam-break, 1M particles (BASELINE.json configs[2]).
+  N > 1: one scene cut into horizontal strips of cell rows, one rank per GPU; default box-fill, 2M particles per GPU
+         (configs[3]: 16M on 8 GPUs); `--scene dam_break_wide --particles 8000000` = configs[4] (64M on 8 GPUs).
+The scene is first RELAXED for `--relax` ticks (default 100, SURVEY.md section 8(d): part of the scene, never timed and
+independent of --warmup), then W warm-up ticks, then K timed ticks.  Timed with CUDA events on the stream the kernels
+are launched on; L2 is flushed between timed steps.  Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -28,18 +32,7 @@ UNIT = "particle-steps/s"
 # algorithmic bytes per particle per kernel for the mixed layout (pos f64x2, vel f32x2, id, p, s,
 # cell id), each record moved once per kernel.  These are the figures `roofline.achieved` is computed from.
 SURVEY_BYTES = {"prepass_wall_key": 20, "place": 14, "rank_gather": 56, "density": 28, "force_integrate": 60}
-
-
-# What THIS design moves per particle per launch: the same accounting plus the records K4 hands
-# to K5 (8 bytes per directed pair, K = measured mean pairs per particle) and the packed (p, s) record.
-def algo_bytes(K):
-    return {
-        "prepass_wall_key": 16 + 4 + 4,                       # R pos; W key, slot
-        "place": 4 + 4 + 4,                                   # R key, slot; W index
-        "rank_gather": (4 + 4 + 16 + 8 + 4) + (16 + 8 + 8 + 4 + 4),   # R idx, key, pos, vel, uid; W pos, rel, vel, uid, key
-        "density": (8 + 4 + 4) + (16 + 4 + 1 + 8 * K),        # R rel, key, uid; W (p, s), pair offset/count, pair records
-        "force_integrate": (16 + 8 + 16 + 4 + 1 + 8 * K) + (16 + 8),   # R pos, vel, (p, s), offset/count, records; W pos, vel
-    }
+DEFAULT_PARTICLES = 1_000_000
 
 
 def peaks():
@@ -47,6 +40,16 @@ def peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(a, world_size):
+    """(scene name, particles per GPU, total particles) - ONE mapping for both arms."""
+    if world_size == 1:
+        return a.scene, a.particles, a.particles
+    default = a.scene == "dam_break" and a.particles == DEFAULT_PARTICLES
+    scene = "box_fill" if default else a.scene
+    per_gpu = a.mgpu_particles if a.particles == DEFAULT_PARTICLES else a.particles
+    return scene, per_gpu, per_gpu * world_size
 
 
 def scene_params(world):
@@ -120,72 +123,117 @@ class ClockSampler:
         return out
 
 
-def run_reference_arm(a):
-    """The reference's CPU implementation of the path on this box's host cores.  The reference itself is pure
-    Python and cannot travel to the GPU box, so this is the oracle port (oracle/step_oracle.c; OpenMP over
-    particles for the force loops, scalar neighbor search), on a bounded sample of the same workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# ---- CPU arms ---------------------------------------------------------------------------------------------------
+def oracle_port_run(scene, n, relax, warmup, steps=None, budget_s=None):
+    """The oracle port (oracle/step_oracle.c; OpenMP over particles for the force loops, scalar neighbor search) on an
+    n-particle instance of `scene`: `relax` + `warmup` untimed ticks, then `steps` timed ticks (or as many as fit
+    `budget_s`).  Returns (particle-steps/s, ticks, seconds, threads)."""
     from oracle import oracle as O
     from sand_crate_b200.scenes import SCENES
-    n = a.cpu_particles
-    world, pos, vel = SCENES[a.scene](n)
-    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
-    cv = coeff_vec(world)
-    kin = np.zeros((1, 5))
-    tick = 0
-    for _ in range(a.warmup):
-        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
-        pos, vel = out["pos_out"], out["vel_out"]
-        tick += 1
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
-        pos, vel = out["pos_out"], out["vel_out"]
-        tick += 1
-    dt = time.perf_counter() - t0
-    value = n * a.steps / dt
-    cores = O.num_threads()
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{a.scene} {a.particles} particles (CPU sample: {n} particles)", "scene": a.scene,
-                   "particles": a.particles},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{a.scene} {n} particles x {a.steps} ticks, oracle/step_oracle.c, {cores} OpenMP threads"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "host": {"cpu_count": os.cpu_count()},
-    }
-    emit(line)
-
-
-def cpu_baseline_sample(scene, budget_s=15.0):
-    """cpu_baseline leg: the oracle port on a bounded sample (about budget_s of CPU work)."""
-    from oracle import oracle as O
-    from sand_crate_b200.scenes import SCENES
-    n = 200_000
     world, pos, vel = SCENES[scene](n)
     seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
     cv = coeff_vec(world)
     kin = np.zeros((1, 5))
-    out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, 0), want_all=False)  # warm
-    pos, vel = out["pos_out"], out["vel_out"]
+    tick = 0
+
+    def one():
+        nonlocal pos, vel, tick
+        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, tick), want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+        tick += 1
+    for _ in range(relax + warmup):
+        one()
     t0 = time.perf_counter()
     ticks = 0
     while True:
-        out = O.step(cv, pos, vel, seg, [4], kin, noise_mode=1, tkey=O.tick_key(0, 1 + ticks), want_all=False)
-        pos, vel = out["pos_out"], out["vel_out"]
+        one()
         ticks += 1
         el = time.perf_counter() - t0
-        if el > budget_s or ticks >= 200:
+        if (steps is not None and ticks >= steps) or (budget_s is not None and (el > budget_s or ticks >= 200)):
             break
-    cores = O.num_threads()
-    return {"value": n * ticks / el, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{scene} {n} particles x {ticks} ticks in {el:.1f}s, oracle/step_oracle.c, {cores} OpenMP threads "
-                      f"(neighbor search scalar).  The reference itself is pure Python: 6.1-7.0e3 particle-steps/s "
-                      f"on one core in the build container (BASELINE.md section 2); it cannot run on the GPU box."}
+    return n * ticks / el, ticks, el, O.num_threads()
+
+
+def _numpy_reference_job(args):
+    """One process: the UNMODIFIED reference `Crate.physics_tick()` (shipped under baseline/_ref, loaded through
+    oracle/ref_shim.py) on a synthetic block of n particles.  Returns (n, ticks, seconds)."""
+    root, scene, n, ticks = args
+    os.environ["SANDCRATE_REFERENCE_ROOT"] = root
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"   # the reference is single-threaded by construction; keep BLAS from pretending otherwise
+    sys.path.insert(0, ROOT)
+    from oracle import ref_shim
+    from sand_crate_b200.scenes import SCENES
+    ref = ref_shim.load_reference()
+    world, pos, vel = SCENES[scene](n)
+    cfg = ref.load_config(os.path.join(ref.config_dir, "wave_machine.yaml"))
+    wc = cfg.world_config
+    wc.rigid_bodies = world.rigid_bodies
+    wc.particle_sources = []
+    wc.coefficients = dict(world.coefficients)
+    crate = ref.Crate(wc)
+    crate.particles = pos.copy()
+    crate.particle_velocities = vel.copy()
+    crate.particles_pressure = np.zeros(len(pos))
+    crate.physics_tick()   # warm
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        crate.physics_tick()
+    return n, ticks, time.perf_counter() - t0
+
+
+def numpy_reference_block(scene):
+    """BASELINE.md section 4 / SURVEY.md section 8(d): the reference's own NumPy step timed on THIS box's host cores:
+    one core at P = 1k / 10k / 100k, and all cores as independent replicas (the step has no intra-tick parallelism)."""
+    root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(root, "src", "crate", "crate.py")):
+        return {"unavailable": "baseline/_ref/ (a copy of the reference tree made by __graft_entry__.build()) is absent"}
+    import multiprocessing as mp
+    ctxmp = mp.get_context("spawn")
+    out = {"impl": "David-Taub/sand_crate src/crate/crate.py Crate.physics_tick(), unmodified, via oracle/ref_shim.py",
+           "unit": UNIT, "one_core": {}}
+    try:
+        with ctxmp.Pool(1) as pool:
+            for n, ticks in ((1_000, 5), (10_000, 3), (100_000, 1)):
+                n_, t_, s_ = pool.apply(_numpy_reference_job, ((root, scene, n, ticks),))
+                out["one_core"][str(n)] = {"value": n_ * t_ / s_, "ticks": t_, "seconds": round(s_, 3)}
+        cores = os.cpu_count() or 1
+        with ctxmp.Pool(cores) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_numpy_reference_job, [(root, scene, 10_000, 2)] * cores)
+            wall = time.perf_counter() - t0
+        out["all_cores_replicas"] = {"cores": cores, "particles_per_replica": 10_000, "ticks": 2,
+                                     "value": sum(n * t / s for n, t, s in res), "wall_s_incl_startup": round(wall, 2)}
+    except Exception as e:  # the block is informative; the arm's own value does not depend on it
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def run_reference_arm(a):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores, same scene mapping
+    as the GPU arm.  The arm's value is the oracle port (all OpenMP threads) on a bounded sample of the workload; the
+    unmodified NumPy reference, which is ~350x slower per core, is timed beside it (`numpy_reference`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    scene, per_gpu, n_total = workload(a, max(world_size, a.gpus))
+    n = a.cpu_particles
+    value, ticks, el, cores = oracle_port_run(scene, n, min(a.relax, 5), a.warmup, steps=a.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * el / ticks, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{scene} {n_total} particles (CPU sample: {n} particles; cost per particle is flat in P)",
+                   "scene": scene, "particles_total": n_total, "particles_per_gpu": per_gpu},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{scene} {n} particles x {ticks} ticks, oracle/step_oracle.c, {cores} OpenMP threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cpu_count": os.cpu_count()},
+    }
+    if not a.no_numpy_reference:
+        line["numpy_reference"] = numpy_reference_block(scene)
+    emit(line)
 
 
 def emit(line: dict) -> None:
@@ -197,6 +245,13 @@ def emit(line: dict) -> None:
 _REAL_STDOUT = 1
 
 
+def load_traffic():
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch and the same capture's kernel durations
+    (profiles/traffic.json, written by profiles/ncu_summary.py from the committed ncu CSV of this bench command)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -205,10 +260,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--relax", type=int, default=100, help="untimed relaxation ticks that are part of the scene")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scene", default="dam_break", choices=["dam_break", "box_fill"])
-    ap.add_argument("--particles", type=int, default=1_000_000)
+    ap.add_argument("--scene", default="dam_break", choices=["dam_break", "box_fill", "dam_break_wide"])
+    ap.add_argument("--particles", type=int, default=DEFAULT_PARTICLES, help="particles (per GPU when --gpus > 1)")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="strip exchange: NCCL send/recv or "
                     "direct NVLink stores into the neighbor's symmetric-memory buffer")
@@ -217,19 +273,21 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=200_000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numpy-reference", action="store_true")
+    ap.add_argument("--no-weak-baseline", action="store_true", help="N > 1: skip the same-scene 1-GPU baseline on rank 0")
     ap.add_argument("--e2e-steps", type=int, default=20)
     a = ap.parse_args()
     if a.impl == "reference":
-        if a.steps == 200 and a.warmup == 100:  # defaults sized for the GPU arm; keep the CPU arm to ~a minute
-            a.steps, a.warmup = 20, 3
-        a.warmup = max(a.warmup, 1)
+        if a.steps == 200:  # default sized for the GPU arm; keep the CPU arm to about a minute
+            a.steps = 20
+        a.warmup = max(a.warmup, 1) if a.warmup != 10 else 3
         return run_reference_arm(a)
     a.warmup = max(a.warmup, 3)
 
     import torch
     import torch.distributed as dist
     from sand_crate_b200 import Crate, _lib
-    from sand_crate_b200.scenes import SCENES
+    from sand_crate_b200.scenes import SCENES, scene_chunks
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -252,83 +310,94 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
     precision = _lib.PRECISION_MIXED if a.precision == "mixed" else _lib.PRECISION_F64
-    dom = None
-    if world_size == 1:
-        n = a.particles
-        scene = a.scene
-        world, pos, vel = SCENES[scene](n)
-        ctx = _lib.Context(n, precision, local_rank, stream)
-        ctx.set_params(**scene_params(world))
-        seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
-        ctx.set_walls(seg, [4], np.zeros((1, 5)))
-        ctx.set_noise(_lib.NOISE_COUNTER, 0)
-        ctx.set_state(pos, vel)
-        step_fn = ctx.step
-        n_total = n
-    else:
-        # one scene cut into horizontal strips of cell rows, NCCL halo + migration exchange every tick
-        # (BASELINE.json configs[3]: box-fill, 2M particles per GPU = 16M on 8 GPUs)
-        from sand_crate_b200.strips import StripDomain
-        scene = "box_fill" if a.scene == "dam_break" and a.particles == 1_000_000 else a.scene
-        per_gpu = a.mgpu_particles if a.particles == 1_000_000 else a.particles
-        n_total = per_gpu * world_size
-        world, pos, vel = SCENES[scene](n_total)
-        dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
-                          device=local_rank, stream=stream, transport=a.transport,
-                          rebalance_every=a.rebalance_every)
-        ctx = dom.ctx
-        step_fn = dom.physics_tick
-        n = n_total // world_size
-        del pos, vel
-
+    scene, n, n_total = workload(a, world_size)
     flush = None if a.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for _ in range(a.warmup):
-        step_fn()
-    barrier()
 
-    def timed_pass(profile):
+    def single_gpu_context(scene_name, count):
+        world_, pos_, vel_ = SCENES[scene_name](count)
+        c_ = _lib.Context(count, precision, local_rank, stream)
+        c_.set_params(**scene_params(world_))
+        seg = np.array(world_.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+        c_.set_walls(seg, [4], np.zeros((1, 5)))
+        c_.set_noise(_lib.NOISE_COUNTER, 0)
+        c_.set_state(pos_, vel_)
+        return world_, c_
+
+    def timed_pass(ctx_, step_fn_, profile, sync_all=True):
         """K steps, each bracketed by CUDA events on the launch stream, L2 flushed (untimed) before each."""
-        ctx.profile_enable(profile)
+        ctx_.profile_enable(profile)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-        barrier()
+        barrier() if sync_all else torch.cuda.synchronize()
         w0 = time.perf_counter()
         for e0, e1 in ev:
             if flush is not None:
                 flush.fill_(1)          # untimed: evicts the previous step's lines from the 126 MB L2
             e0.record()
-            step_fn()
+            step_fn_()
             e1.record()
-        barrier()
+        barrier() if sync_all else torch.cuda.synchronize()
         w = time.perf_counter() - w0
         ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
-        kern = ctx.profile_read() if profile else {}
-        ctx.profile_enable(False)
+        kern = ctx_.profile_read() if profile else {}
+        ctx_.profile_enable(False)
         return float(ms.sum()), w, kern
+
+    dom = None
+    if world_size == 1:
+        world, ctx = single_gpu_context(scene, n)
+        step_fn = ctx.step
+    else:
+        from sand_crate_b200.strips import StripDomain
+        world, chunks = scene_chunks(scene, n_total)
+        dom = StripDomain(world, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
+                          device=local_rank, stream=stream, transport=a.transport,
+                          rebalance_every=a.rebalance_every, chunks=chunks)
+        ctx = dom.ctx
+        step_fn = dom.physics_tick
+
+    for _ in range(a.relax + a.warmup):   # relaxation is part of the scene; then W warm-up ticks
+        step_fn()
+    barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launch_count()
     # pass 1 = THE timed region (value, ms_per_step): plain launches, nothing but the step kernels on the stream
-    total_ms, wall, _ = timed_pass(False)
+    total_ms, wall, _ = timed_pass(ctx, step_fn, False)
     launches = ctx.launch_count() - launches0
     # pass 2 = the same K steps again with a CUDA-event pair around every kernel launch (per-kernel durations for
     # the roofline); the extra event records stretch the gaps between kernels, so its step time is not the headline
-    total_ms_prof, _, kernels = timed_pass(True)
+    total_ms_prof, _, kernels = timed_pass(ctx, step_fn, True)
     clocks = sampler.stop()
-    n_live = ctx.particle_count() if dom is None else dom.status()["n_local"]
-    if dom is None:   # mean directed pairs per particle of the last tick (sizes the pair records in the byte model)
-        counts, _ = ctx.get_neighbors(n_live)
-        mean_pairs = float(counts.mean())
-        del counts
-    else:
-        mean_pairs = 5.3  # strip mode has no tap; rest-density value measured on one GPU
-    dist_status = None if dom is None else dom.status()
+    status = {"overflow": False, "too_far": False, "n_local": ctx.particle_count()} if dom is None else dom.status()
+    n_live = status["n_local"]
+    n_pairs = ctx.last_pair_count()
+    mean_pairs = n_pairs / max(n_live, 1)   # directed pairs per local particle of the last tick (ghosts included)
+    untiled = ctx.untiled_blocks()
 
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = n_total * a.steps / (total_ms_max * 1e-3)
+    per_rank = None
+    if world_size > 1:
+        per_rank = [None] * world_size
+        dist.all_gather_object(per_rank, {"rank": rank, "n_local": int(n_live), "ms_per_step": total_ms / a.steps,
+                                          "overflow": bool(status["overflow"]), "too_far": bool(status["too_far"]),
+                                          "rows": [int(dom.row_lo), int(dom.row_hi)], "mean_pairs": mean_pairs})
+
+    # ---- N > 1: the same per-GPU workload on ONE GPU, inside this invocation, as the weak-scaling baseline ---------
+    weak = None
+    if world_size > 1 and not a.no_weak_baseline:
+        if rank == 0:
+            _, c1 = single_gpu_context(scene, n)
+            for _ in range(a.relax + a.warmup):
+                c1.step()
+            ms1, _, _ = timed_pass(c1, c1.step, False, sync_all=False)
+            weak = ms1 / a.steps
+            c1.close()
+        barrier()
 
     # ---- e2e: the public API with host buffers: upload state, tick, read the result back, every step ----------
     if dom is None:
@@ -344,11 +413,12 @@ def main():
             return crate.particles
         e2e_api = "Crate.set_particles(host, page-locked) -> physics_tick() -> Crate.particles (host, page-locked)"
     else:
-        uid0, gp, gv = dom.owned()
+        gp, gv, uid0 = dom.ctx.dist_get_owned()
         m = len(uid0)
         hp = torch.empty((m, 2), dtype=torch.float64, pin_memory=True).numpy()
         hv = torch.empty((m, 2), dtype=torch.float64, pin_memory=True).numpy()
         hp[:], hv[:] = gp, gv
+        del gp, gv
 
         def e2e_step():
             dom.ctx.set_state_uids(hp, hv, uid0)
@@ -376,34 +446,39 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        ALGO_BYTES = algo_bytes(mean_pairs)
-        top = max((k for k in kernels if k in ALGO_BYTES), key=lambda k: kernels[k]["ms"], default="density")
+        top = max((k for k in kernels if k in SURVEY_BYTES), key=lambda k: kernels[k]["ms"], default="density")
         k = kernels.get(top, {"launches": 1, "ms": float("nan")})
         k_ms = k["ms"] / max(k["launches"], 1)
         achieved = SURVEY_BYTES[top] * n_live / (k_ms * 1e-3) / 1e9
-        design_achieved = ALGO_BYTES[top] * n_live / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top)
+        traffic_all = load_traffic()
+        tr = traffic_all.get(top) if isinstance(traffic_all.get(top), dict) else None
         per_kernel = {}
         for name, v in kernels.items():
             ms = v["ms"] / max(v["launches"], 1)
             per_kernel[name] = {"ms": round(ms, 5), "launches_per_step": round(v["launches"] / a.steps, 2)}
             if name in SURVEY_BYTES:
-                per_kernel[name]["algo_gbs"] = round(SURVEY_BYTES[name] * n_live / (ms * 1e-3) / 1e9, 1)
-                per_kernel[name]["design_gbs"] = round(ALGO_BYTES[name] * n_live / (ms * 1e-3) / 1e9, 1)
+                gbs = SURVEY_BYTES[name] * n_live / (ms * 1e-3) / 1e9
+                per_kernel[name]["algo_gbs"] = round(gbs, 1)
+                per_kernel[name]["frac"] = round(gbs / peak, 4)
+        step_ms = total_ms_max / a.steps
+        if dom is None:
+            parallelism = "single GPU"
+        else:
+            how = ("direct NVLink stores into the neighbor's symmetric-memory buffer + release/acquire flags (no NCCL call "
+                   "per tick)" if dom.transport == "p2p" else "NCCL send/recv (batch_isend_irecv)")
+            parallelism = (f"{world_size} horizontal strips of cell rows, halo + migration exchange with rank+-1 every "
+                           f"tick by {how}; halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, re-cut "
+                           f"every {dom.rebalance_every or 'never'}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": total_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 forces / f64 positions" if a.precision == "mixed" else "f64", "data": "synthetic",
-            "config": {"workload": f"{scene} {n_total} particles ({n} per GPU), closed unit box, counter noise 0.1",
-                       "scene": scene, "particles_total": n_total, "particles_per_gpu": n,
-                       "local_particles_rank0": n_live,
-                       "parallelism": "single GPU" if world_size == 1 else
-                       f"{world_size} horizontal strips of cell rows, NCCL send/recv halo + migration with rank+-1 "
-                       f"every tick (halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, transport {dom.transport}, re-cut every {dom.rebalance_every or 'never'})",
-                       "dist_status_rank0": dist_status,
+            "config": {"workload": f"{scene} {n_total} particles ({n} per GPU), closed unit box, counter noise 0.1, "
+                                   f"{a.relax} relaxation ticks before the warm-up",
+                       "scene": scene, "particles_total": n_total, "particles_per_gpu": n, "relax_ticks": a.relax,
+                       "local_particles_rank0": n_live, "mean_pairs_per_particle": round(mean_pairs, 3),
+                       "untiled_density_blocks": untiled,
+                       "parallelism": parallelism,
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks"},
             "clocks": clocks,
@@ -411,21 +486,36 @@ def main():
                     "d2h_bytes_per_step": d2h_bytes, "steps": a.e2e_steps, "api": e2e_api},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_particle": SURVEY_BYTES[top], "kernel_ms": k_ms,
-                         "note": "K4 is issue-bound, not HBM-bound (ncu: 74 % issue-active at 22 of 32 lanes, 6 % DRAM; profiles/r1u_ncu_full_summary.csv)",
-                         "design": {"bytes_per_particle": ALGO_BYTES[top], "achieved": design_achieved,
-                                    "frac": design_achieved / peak, "mean_pairs_per_particle": mean_pairs},
+                         "frac": achieved / peak, "traffic": None if tr is None else tr.get("dram_bytes"),
+                         "peak_source": peak_src, "algorithmic_bytes_per_particle": SURVEY_BYTES[top],
+                         "algorithmic_bytes_per_launch": SURVEY_BYTES[top] * n_live, "kernel_ms": k_ms,
+                         "traffic_source": None if tr is None else {
+                             k2: tr.get(k2) for k2 in ("ncu_csv", "ncu_kernel_us", "particles", "note")},
                          "whole_step": {"survey_bytes_per_particle": 178,
-                                        "achieved": 178 * n_live / (total_ms_max / a.steps * 1e-3) / 1e9,
-                                        "design_bytes_per_particle": sum(ALGO_BYTES.values()),
-                                        "design_achieved": sum(ALGO_BYTES.values()) * n_live / (total_ms_max / a.steps * 1e-3) / 1e9}},
+                                        "achieved": 178 * n_live / (step_ms * 1e-3) / 1e9,
+                                        "frac": 178 * n_live / (step_ms * 1e-3) / 1e9 / peak}},
             "kernels": per_kernel,
             "wall_s_timed_region": wall,
             "ms_per_step_with_per_kernel_events": total_ms_prof / a.steps,
         }
+        if per_rank is not None:
+            nl = [p["n_local"] for p in per_rank]
+            line["strips"] = {"n_local_min": min(nl), "n_local_max": max(nl),
+                              "imbalance": round(max(nl) / (sum(nl) / len(nl)), 4),
+                              "overflow": any(p["overflow"] for p in per_rank),
+                              "too_far": any(p["too_far"] for p in per_rank), "per_rank": per_rank}
+        if weak is not None:
+            line["weak_baseline_1gpu_ms"] = weak
+            line["efficiency_same_scene"] = weak / step_ms
+            line["config"]["weak_baseline"] = (f"{scene} {n} particles on one GPU (rank 0), same relaxation, warm-up, "
+                                               f"steps and L2 flush, inside this invocation")
         if not a.no_cpu_baseline and world_size == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(a.scene)
+            v, ticks, el, cores = oracle_port_run(a.scene, a.cpu_particles, 1, 1, budget_s=15.0)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{a.scene} {a.cpu_particles} particles x {ticks} ticks in {el:.1f}s, oracle/step_oracle.c, {cores} "
+                          f"OpenMP threads (neighbor search scalar).  The unmodified NumPy reference is timed by "
+                          f"`bench.py --impl reference` (numpy_reference block)."}
         emit(line)
     if world_size > 1:
         dist.destroy_process_group()

@@ -143,6 +143,15 @@ int sc_profile_enable(sc_ctx *ctx, int on);
 int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int slots);
 const char *sc_profile_name(int slot);
 int64_t sc_launch_count(const sc_ctx *ctx); /* kernels launched by this context so far */
+/* sum(K_i) of the last tick = rows of the reference's `colliders` lists (crate.py:161-175) over the particles this
+ * context holds (ghost copies of a strip included).  Synchronises. */
+int sc_last_pair_count(sc_ctx *ctx, int64_t *n_pairs);
+
+/* ---- diagnostics (developer aids; no reference counterpart, results are never affected) ---------------------- */
+/* re-run the density (which = 4) or force (which = 5) kernel of the last tick `reps` times; mean milliseconds */
+double sc_debug_rerun(sc_ctx *ctx, int which, int reps);
+/* blocks of the tiled density kernel that ran in pass-through mode in the last tick (windows too large to stage) */
+int64_t sc_debug_untiled_blocks(sc_ctx *ctx);
 
 /* ---- multi-GPU strip decomposition (one context per rank; the transport is the caller's: NCCL send/recv) ------ */
 /* The reference's search is already a 1-D strip decomposition in y with strip height one diameter
@@ -156,7 +165,11 @@ int64_t sc_launch_count(const sc_ctx *ctx); /* kernels launched by this context 
  *   sc_dist_unpack  appends received migrants as owned particles and received halos as ghosts
  * A ghost is simulated like any particle and discarded by the next pack.  With halo_rows >= 4 every owned particle
  * sees the neighbors, pressures and normals of the global computation in the same order: SC_PRECISION_F64 results
- * are bit-identical to a single-GPU run.  Noise must be SC_NOISE_COUNTER or SC_NOISE_NONE.  uids must be < 2^31. */
+ * are bit-identical to a single-GPU run.
+ * Restrictions of the strip mode: noise must be SC_NOISE_COUNTER or SC_NOISE_NONE (the reference's global RNG
+ * stream cannot be split across ranks); uids must be < 2^31 (bit 31 marks a ghost copy); the host mirror
+ * (sand_crate_b200/strips.py) additionally requires closed scenes (no particle sources) and fixed walls; on a context
+ * with a neighbor, sc_get_state / sc_get_uids / the parity taps return an error - read back with sc_dist_get_owned. */
 int64_t sc_dist_wire_bytes(int64_t wire_capacity);
 int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t row_hi, int halo_rows,
                       int64_t wire_capacity);

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY - generates tests/golden/*.npz by executing the UNMODIFIED reference
 (David-Taub/sand_crate, loaded from /root/reference through oracle/ref_shim.py) in the build container.
 
-    python -m oracle.make_golden            # everything (a few minutes: wave_machine to tick 500)
+    python -m oracle.make_golden            # everything (~30 minutes: wave_machine to tick 3000)
     python -m oracle.make_golden --quick    # skip wave_machine beyond tick 100
 
 The fixtures are committed; the GPU box never needs /root/reference.
@@ -34,14 +34,15 @@ sys.path.insert(0, ROOT)
 from oracle.ref_shim import RecordingCrate, load_reference  # noqa: E402
 
 STEP_TICKS = {
-    "stirring_cup": [1, 20, 60, 150, 199, 260, 400],
-    "wave_machine": [5, 100, 300, 500],
+    "stirring_cup": [1, 20, 60, 150, 199, 260, 400, 800, 1199],
+    "wave_machine": [5, 100, 300, 500, 1000, 2000, 2999],
     "free_body": [],
 }
 MONITOR_SECTIONS = ("tension", "gravity", "pressure", "viscosity", "wall_bounce", "continuous_collision")
 FREERUN_TICKS = {
-    "stirring_cup": [1, 5, 20, 40, 80],
-    "wave_machine": [1, 5, 20, 40],
+    # up to the configs' own `ticks_to_record` (config/stirring_cup.yaml:3 = 1200, config/wave_machine.yaml:3 = 3000)
+    "stirring_cup": [1, 5, 20, 40, 80, 200, 400, 800, 1200],
+    "wave_machine": [1, 5, 20, 40, 500, 1000, 2000, 3000],
     "free_body": [1, 10, 30, 60],
 }
 

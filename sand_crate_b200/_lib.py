@@ -87,6 +87,9 @@ SIGNATURES = {
     "sc_profile_read": (C.c_int, [_ctx, _lp, _dp, C.c_int]),
     "sc_profile_name": (C.c_char_p, [C.c_int]),
     "sc_launch_count": (C.c_int64, [_ctx]),
+    "sc_last_pair_count": (C.c_int, [_ctx, _lp]),
+    "sc_debug_rerun": (C.c_double, [_ctx, C.c_int, C.c_int]),
+    "sc_debug_untiled_blocks": (C.c_int64, [_ctx]),
 }
 
 _lib = None
@@ -413,6 +416,14 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._L.sc_launch_count(self._h))
+
+    def last_pair_count(self) -> int:
+        n = C.c_int64()
+        self._ck(self._L.sc_last_pair_count(self._h, C.byref(n)))
+        return n.value
+
+    def untiled_blocks(self) -> int:
+        return int(self._L.sc_debug_untiled_blocks(self._h))
 
 
 def wire_bytes(wire_capacity: int) -> int:

@@ -20,7 +20,7 @@ HEADERS = ["sc_common.cuh", "sc_pair.cuh", "sc_tile.cuh", "sc_sort.cuh", "sc_dis
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "--shared", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "--shared", "-Xptxas", "-v", "-ldl",
 ]
 
 

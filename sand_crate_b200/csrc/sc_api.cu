@@ -1,6 +1,7 @@
 // sc_api.cu - context, launch orchestration and the C ABI declared in include/sandcrate.h.
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see sand_crate_b200/build.py).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdio>
@@ -17,11 +18,20 @@ static std::string g_create_error;
 
 enum Slot {
     SLOT_CLEAR = 0, SLOT_PREPASS, SLOT_SCAN, SLOT_PLACE, SLOT_RANK_GATHER, SLOT_DENSITY, SLOT_FORCE, SLOT_COUNT,
-    SLOT_RANKMAP, SLOT_IO, SLOT_END
+    SLOT_RANKMAP, SLOT_IO, SLOT_END, SLOT_DIST_PACK, SLOT_DIST_PUSH, SLOT_DIST_UNPACK
 };
 static const char *k_slot_names[SC_PROFILE_SLOTS] = {
     "clear", "prepass_wall_key", "scan", "place", "rank_gather", "density", "force_integrate", "count_neighbors",
-    "rank_map", "io_scatter", "end_tick", "", "", "", "", ""};
+    "rank_map", "io_scatter", "end_tick", "dist_pack", "dist_push", "dist_unpack", "", ""};
+// NVTX range per launch, named after the section of the reference's tick the kernel replaces (the `debug_timer`
+// sections of crate.py:97-124, utils/timer.py:10-48) so a timeline reads like the reference's own Timer overlay
+static const char *k_slot_nvtx[SC_PROFILE_SLOTS] = {
+    "begin tick (clear cell grid)", "Virtual Colliders (remove, walls, hard wall fix, cell keys)",
+    "Collisions: cell scan", "Collisions: counting-sort placement", "Collisions: in-cell rank + gather",
+    "Collisions + Colliders + Pressure + tension pass 1 (density kernel)",
+    "tension, gravity, pressure, viscosity, wall_bounce, continuous_collision, integrate (force kernel)",
+    "tap: neighbor counts", "readback: uid -> row map", "readback / upload", "end tick",
+    "strips: pack", "strips: NVLink push", "strips: unpack", "", ""};
 
 struct ProfEvent { int slot; cudaEvent_t e0, e1; };
 
@@ -138,6 +148,7 @@ struct ProfScope {
     sc_ctx *c; int slot; cudaEvent_t e0 = nullptr, e1 = nullptr;
     ProfScope(sc_ctx *c_, int slot_) : c(c_), slot(slot_) {
         c->launches++;
+        nvtxRangePushA(k_slot_nvtx[slot]);  // a no-op unless a profiler has injected itself
         if (!c->profiling) return;
         auto get = [&]() {
             cudaEvent_t e;
@@ -148,6 +159,7 @@ struct ProfScope {
         cudaEventRecord(e0, c->stream);
     }
     ~ProfScope() {
+        nvtxRangePop();
         if (!c->profiling) return;
         cudaEventRecord(e1, c->stream);
         c->pending.push_back({slot, e0, e1});
@@ -458,6 +470,9 @@ static int sync_count(sc_ctx *ctx) {
 
 static int upload_particles(sc_ctx *ctx, const double *pos, const double *vel, int64_t at, int64_t n) {
     if (n == 0) return 0;
+    // bit 31 of a uid marks a ghost copy (sc_dist.cuh) and the uid -> row map grows with every particle ever created
+    if ((uint64_t)ctx->next_uid + (uint64_t)n >= (uint64_t)SC_GHOST_BIT)
+        return fail(ctx, "particle identities exhausted (2^31 particles created in this context)");
     CK(cudaMemcpyAsync(ctx->pos_cur + at, pos, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->precision == SC_PRECISION_F64) {
         CK(cudaMemcpyAsync((double2 *)ctx->vel_cur + at, vel, sizeof(double2) * (size_t)n, cudaMemcpyHostToDevice,
@@ -599,7 +614,8 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
         const uint32_t scan_words = (g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;  // ticket + descriptors
         CK(launch_pdl(k_begin_tick, dim3(nb), dim3(SC_BLOCK), ctx->stream, ctx->cnt, ctx->cell_start, g.ncells,
-                      ctx->carry_count ? 1 : 0, ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum, scan_words));
+                      ctx->carry_count ? 1 : 0, ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum, scan_words,
+                      (uint32_t)ctx->cap));
         ctx->carry_count = false;
     }
     if (n > 0) {
@@ -812,6 +828,14 @@ extern "C" int sc_synchronize(sc_ctx *ctx) {
 
 // ---------------------------------------------------------------------------------------------------------
 // readback (original index order)
+// The uid -> row map is sized from THIS context's uids.  A strip with neighbors also holds ghosts (bit 31 set) and
+// migrants with other ranks' uids, which would index far outside it: those contexts read back through
+// sc_dist_get_owned instead.
+static int no_neighbors(sc_ctx *ctx, const char *who) {
+    if (ctx->dist_on && (ctx->dist.has_lo || ctx->dist.has_hi))
+        return fail(ctx, std::string(who) + ": not available on a strip with neighbors (use sc_dist_get_owned)");
+    return 0;
+}
 static int ensure_rank_for_current(sc_ctx *ctx) {
     // the current state's uid array is uid_cur and its live count is cnt->n
     if (!ctx->rank_valid) {
@@ -825,6 +849,7 @@ extern "C" int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *press
     if (!ctx) return fail(ctx, "sc_get_state: NULL ctx");
     CK(cudaSetDevice(ctx->device));
     if (ctx->in_step) return fail(ctx, "sc_get_state: inside a split step");
+    CKR(no_neighbors(ctx, "sc_get_state"));
     CKR(sync_count(ctx));
     const int64_t n = ctx->n_host;
     if (n_out) *n_out = n;
@@ -867,6 +892,7 @@ extern "C" int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n_o
     if (!ctx) return fail(ctx, "sc_get_uids: NULL ctx");
     CK(cudaSetDevice(ctx->device));
     if (ctx->in_step) return fail(ctx, "sc_get_uids: inside a split step");
+    CKR(no_neighbors(ctx, "sc_get_uids"));
     CKR(sync_count(ctx));
     const int64_t n = ctx->n_host;
     if (n_out) *n_out = n;
@@ -885,6 +911,7 @@ static int tap_prologue(sc_ctx *ctx, const char *who, int64_t cap, int64_t *n_ou
     if (!ctx) return fail(ctx, std::string(who) + ": NULL ctx");
     CK(cudaSetDevice(ctx->device));
     if (!ctx->srt_valid) return fail(ctx, std::string(who) + ": no search state (call sc_step or sc_step_begin first)");
+    CKR(no_neighbors(ctx, who));
     uint32_t total = 0;
     CK(cudaMemcpyAsync(&total, ctx->cell_start + ctx->grid.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1041,8 +1068,20 @@ extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int6
     return 0;
 }
 
-// ---- developer aid (not part of the ABI in include/sandcrate.h): re-run one pair kernel of the last tick `reps` times
-// and return the mean milliseconds.  K4 and K5 only read the sorted set, so re-running them is harmless.
+// directed pairs sum(K_i) of the last tick over the particles this context holds (ghosts included), = the number of
+// pair records the density kernel handed to the force kernel.  Synchronises.
+extern "C" int sc_last_pair_count(sc_ctx *ctx, int64_t *n_pairs) {
+    if (!ctx || !n_pairs) return fail(ctx, "sc_last_pair_count: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    Counters h;
+    CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_pairs = (int64_t)h.pair_cursor;
+    return 0;
+}
+
+// ---- developer aids (declared in include/sandcrate.h under "diagnostics"): re-run one pair kernel of the last tick
+// `reps` times and return the mean milliseconds.  K4 and K5 only read the sorted set, so re-running them is harmless.
 extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
     if (!ctx || !ctx->srt_valid) return -1.0;
     cudaSetDevice(ctx->device);
@@ -1234,7 +1273,7 @@ extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     ctx->carry_count = false;
     const int64_t n = ctx->n_host;
     if (n > 0) {
-        ProfScope ps(ctx, SLOT_IO);
+        ProfScope ps(ctx, SLOT_DIST_PACK);
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_maybe_pdl(dist_pdl_mask() & 1, k_dist_pack<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
                 ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, lo, hi));
@@ -1253,7 +1292,7 @@ static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo,
     UnpackSide lo{ctx->dist.has_lo ? (const WireHeader *)recv_lo : nullptr, (const uint32_t *)flag_lo};
     UnpackSide hi{ctx->dist.has_hi ? (const WireHeader *)recv_hi : nullptr, (const uint32_t *)flag_hi};
     if (lo.hdr || hi.hdr) {
-        ProfScope ps(ctx, SLOT_IO);
+        ProfScope ps(ctx, SLOT_DIST_UNPACK);
         const dim3 grid(blocks_for(ctx->dist.cap), 2);
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<double>, grid, dim3(SC_BLOCK), ctx->stream,
@@ -1298,7 +1337,7 @@ extern "C" int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_rec
         hi.src = (const WireHeader *)send_hi_dev; hi.peer_dst = peer_recv_hi_dev; hi.peer_flag = (uint32_t *)peer_flag_hi_dev;
     }
     if (!lo.src && !hi.src) return 0;
-    ProfScope ps(ctx, SLOT_IO);
+    ProfScope ps(ctx, SLOT_DIST_PUSH);
     const size_t bytes = sizeof(WireHeader) + (size_t)ctx->dist.cap * sizeof(WireRec);
     const unsigned nb = (unsigned)std::min<size_t>((bytes / 16 + SC_BLOCK - 1) / SC_BLOCK, 64);
     CK(launch_maybe_pdl(dist_pdl_mask() & 2, k_wire_push, dim3(nb, 2), dim3(SC_BLOCK), ctx->stream, lo, hi, ctx->dist.cap, value));

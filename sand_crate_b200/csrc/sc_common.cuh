@@ -1,13 +1,9 @@
 // sc_common.cuh - shared device-side definitions for the SandCrate particle step on sm_100a.
 //
 // Everything here restates ONE reference tick (David-Taub/sand_crate src/crate/crate.py:91-129) as per-particle
-// device functions.  The file is compiled into two translation units:
-//   sc_kernels_f64.cu  (-fmad=false)  Real = double: NumPy never fuses multiply-add, so neither may we
-//   sc_kernels_f32.cu                 Real = float : production mode, positions stay fp64 in HBM
+// device functions.  One translation unit (sc_api.cu), compiled with -fmad=false: NumPy never fuses multiply-add, so
+// the fp64 parity kernels may not either; the fp32 production kernels spell out fmaf() where fusion is wanted.
 #pragma once
-#ifdef SC_NO_RESTRICT
-#define
-#endif
 #include <cuda_runtime.h>
 #include <stdint.h>
 

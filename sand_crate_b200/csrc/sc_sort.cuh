@@ -413,11 +413,14 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
 __global__ void __launch_bounds__(SC_BLOCK)
 k_begin_tick(Counters *cnt, uint32_t *cell_count, uint32_t ncells, int carry_count,
              uint32_t *bits_a, uint32_t *bits_b, uint32_t nbits_words,
-             unsigned long long *scan_desc, uint32_t scan_words) {
+             unsigned long long *scan_desc, uint32_t scan_words, uint32_t cap) {
     pdl_enter();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
+        // the strip exchange appends with an atomic counter and only flags an overflow: every later kernel bounds its
+        // indices by cnt->n, so the count itself must never exceed the arrays
+        if (cnt->n > cap) { cnt->n = cap; cnt->overflow = 1u; }
         cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0; cnt->n_untiled = 0;
     }
     uint4 *c4 = reinterpret_cast<uint4 *>(cell_count);

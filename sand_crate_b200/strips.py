@@ -68,17 +68,40 @@ def cuts_from_histogram(hist: np.ndarray, row0: int, nranks: int, halo_rows: int
     return cuts
 
 
+def partition_histogram(hist: np.ndarray, row0: int, nranks: int, halo_rows: int = HALO_ROWS) -> list[int]:
+    """`partition_rows` from a per-row histogram (`hist[k]` = particles in row `row0 + k`)."""
+    nz = np.nonzero(hist)[0]
+    lo, hi = row0 + int(nz[0]), row0 + int(nz[-1])
+    cuts = cuts_from_histogram(hist[nz[0]:nz[-1] + 1], lo, nranks, halo_rows)
+    if nranks > 1 and cuts[-2] + 2 * halo_rows > hi + 1:
+        raise ValueError(f"scene has too few cell rows ({hi - lo + 1}) for {nranks} strips of >= {2 * halo_rows} rows")
+    return cuts
+
+
+def world_rows(particle_radius: float) -> tuple[int, int]:
+    """(first row, number of rows) covering every position a live particle can have (crate.py:152: -r <= y <= 1 + r,
+    plus the wall fix's shift of < r)."""
+    d = 2 * particle_radius
+    row0 = int(np.floor(-2 * particle_radius / d)) - 1
+    return row0, int(np.floor((1 + 2 * particle_radius) / d)) + 2 - row0
+
+
 class StripDomain:
     """One rank's share of a strip-decomposed scene.
 
-    `world` is a WorldConfig (closed scenes: no particle sources), `pos` / `vel` the WHOLE initial scene (every rank
-    generates it from the same seed and keeps its rows), uids are the global row indices of `pos`."""
+    `world` is a WorldConfig (closed scenes: no particle sources).  The initial scene comes either as `pos` / `vel`
+    (the WHOLE scene, every rank generates it from the same seed and keeps its rows) or as `chunks` (a callable returning
+    an iterator of (first row index, positions): `scenes.scene_chunks`; velocities zero) - the form the 16M / 64M scenes
+    use, so that no rank ever holds the whole scene.  uids are the global row indices of the scene.
 
-    def __init__(self, world, pos, vel, *, rank: int, world_size: int, precision: str = "mixed",
+    Restrictions of the strip mode (they hold for the synthetic multi-GPU configs): closed scenes, fixed walls,
+    counter or no noise."""
+
+    def __init__(self, world, pos=None, vel=None, *, rank: int, world_size: int, precision: str = "mixed",
                  noise: str = "counter", noise_seed: int = 0, device: int = 0, stream: int | None = None,
                  halo_rows: int = HALO_ROWS, slack: float = 1.3, wire_capacity: int | None = None,
                  context_factory=None, tensor_device=None, comm=None, transport: str = "nccl",
-                 rebalance_every: int = 0, cuts: list | None = None):
+                 rebalance_every: int = 0, cuts: list | None = None, chunks=None, check_every: int = 256):
         import torch
 
         if world.particle_sources:
@@ -90,16 +113,52 @@ class StripDomain:
         self.halo_rows = halo_rows
         c = world.coefficients
         self.diameter = 2 * c["particle_radius"]
-        rows = rows_of(pos, self.diameter)
-        self.cuts = list(cuts) if cuts is not None else partition_rows(rows, world_size, halo_rows)
+        self._row0, self._nrows = world_rows(c["particle_radius"])
+        if chunks is None:
+            whole_pos, whole_vel = np.asarray(pos, dtype=np.float64), np.asarray(vel, dtype=np.float64)
+            chunks = lambda: iter([(0, whole_pos)])  # noqa: E731
+        else:
+            whole_vel = None
+        # pass 1: per-row histogram of the whole scene -> equal-count cuts, capacities
+        hist = np.zeros(self._nrows, np.int64)
+        n_total = 0
+        for _, p in chunks():
+            r = np.clip(rows_of(p, self.diameter) - self._row0, 0, self._nrows - 1)
+            hist += np.bincount(r, minlength=self._nrows)
+            n_total += len(p)
+        self.cuts = list(cuts) if cuts is not None else partition_histogram(hist, self._row0, world_size, halo_rows)
         assert len(self.cuts) == world_size + 1
         self.row_lo, self.row_hi = self.cuts[rank], self.cuts[rank + 1]
-        mine = np.nonzero((rows >= self.row_lo) & (rows < self.row_hi))[0]
-        per_row = max(int(np.bincount(rows - rows.min()).max()), 1)
+        # pass 2: this rank's rows
+        keep_uid, keep_pos, keep_vel = [], [], []
+        for i0, p in chunks():
+            r = rows_of(p, self.diameter)
+            m = np.nonzero((r >= self.row_lo) & (r < self.row_hi))[0]
+            keep_uid.append((m + i0).astype(np.uint32))
+            keep_pos.append(p[m])
+            keep_vel.append(whole_vel[m + i0] if whole_vel is not None else np.zeros((len(m), 2)))
+        mine = np.concatenate(keep_uid)
+        pos_mine, vel_mine = np.concatenate(keep_pos), np.concatenate(keep_vel)
+        del keep_uid, keep_pos, keep_vel
+        self.n_total = n_total
+        per_row = max(int(hist.max()), 1)
         self.wire_capacity = int(wire_capacity or max(4 * (halo_rows + 2) * per_row, 1024))
         # room for this rank's share after re-balancing as well as for an unbalanced start
-        capacity = int(max(len(mine), -(-len(rows) // world_size)) * slack) + 2 * self.wire_capacity + 1024
+        capacity = int(max(len(mine), -(-n_total // world_size)) * slack) + 2 * self.wire_capacity + 1024
         self.wire_capacity = min(self.wire_capacity, capacity)
+        self._torch_stream = None
+        if context_factory is None:
+            # The context launches on ONE stream and everything torch does for this domain (wire-buffer allocation,
+            # NCCL send / recv, the re-cut all-reduce) must be ordered against it.  So the domain owns the choice: a
+            # caller's stream handle is wrapped, otherwise a torch stream is created; exchange() runs under it.
+            # (Handle 0 / None used to make the library open a private stream that NCCL never saw: stale halos.)
+            if stream:
+                self._torch_stream = torch.cuda.ExternalStream(int(stream), device=torch.device("cuda", device))
+            else:
+                self._torch_stream = torch.cuda.Stream(device=torch.device("cuda", device))
+                stream = self._torch_stream.cuda_stream
+            if not stream:
+                raise ValueError("strip decomposition needs a non-default CUDA stream")
         factory = context_factory or _lib.Context
         prec = {"f64": _lib.PRECISION_F64, "mixed": _lib.PRECISION_MIXED}[precision]
         self.ctx = factory(capacity, prec, device, stream)
@@ -116,25 +175,26 @@ class StripDomain:
         seg = np.vstack([b.segments for b in bodies]) if bodies else np.zeros((0, 2, 2))
         self.ctx.set_walls(seg, [len(b) for b in bodies], np.array([b.kinematics() for b in bodies]).reshape(-1, 5))
         self.ctx.set_noise({"counter": _lib.NOISE_COUNTER, "none": _lib.NOISE_NONE}[noise], noise_seed)
-        self.ctx.set_state_uids(pos[mine], vel[mine], mine.astype(np.uint32))
+        self.ctx.set_state_uids(pos_mine, vel_mine, mine)
+        del pos_mine, vel_mine, mine
         self.ctx.dist_configure(rank, world_size, self.row_lo, self.row_hi, halo_rows, self.wire_capacity)
         self.tick = 0
         # re-balancing: every `rebalance_every` ticks the per-row histogram is summed over the ranks (the scheme's
         # only collective) and the cuts then SLIDE towards the new equal-count positions by at most halo - 2 rows per
         # tick, so the rows a cut hands over travel as ordinary migrants
         self.rebalance_every = int(rebalance_every)
+        self.check_every = int(check_every)   # poll the device's overflow / too_far flags this often (synchronises)
         self.target_cuts = list(self.cuts)
         self.max_cut_shift = max(halo_rows - 2, 1)
-        self._row0 = int(np.floor(-2 * c["particle_radius"] / self.diameter)) - 1
-        self._nrows = int(np.floor((1 + 2 * c["particle_radius"]) / self.diameter)) + 2 - self._row0
         self._tensor_device = tensor_device
 
         nbytes = _lib.wire_bytes(self.wire_capacity) if context_factory is None else 16 + 40 * self.wire_capacity
         dev = tensor_device if tensor_device is not None else torch.device("cuda", device)
-        mk = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # noqa: E731
         self.has_lo, self.has_hi = rank > 0, rank < world_size - 1
-        self.send_lo, self.recv_lo = (mk(), mk()) if self.has_lo else (None, None)
-        self.send_hi, self.recv_hi = (mk(), mk()) if self.has_hi else (None, None)
+        with self._on_stream():
+            mk = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # noqa: E731
+            self.send_lo, self.recv_lo = (mk(), mk()) if self.has_lo else (None, None)
+            self.send_hi, self.recv_hi = (mk(), mk()) if self.has_hi else (None, None)
         self._comm = comm  # torch.distributed module or a test double with batch_isend_irecv / P2POp / isend / irecv
         if transport not in ("nccl", "p2p", "auto"):
             raise ValueError("transport must be 'nccl', 'p2p' or 'auto'")
@@ -142,7 +202,8 @@ class StripDomain:
         self._symm = None
         if transport in ("p2p", "auto") and world_size > 1 and context_factory is None:
             try:
-                self._setup_p2p(nbytes, dev)
+                with self._on_stream():
+                    self._setup_p2p(nbytes, dev)
                 ok = 1
             except Exception:  # no peer access / no symmetric memory on this box
                 if transport == "p2p":
@@ -157,6 +218,14 @@ class StripDomain:
                 self.transport = "p2p" if self._symm is not None else "nccl"
         elif transport == "auto":
             self.transport = "nccl"
+
+    def _on_stream(self):
+        """Context manager: torch work issued inside is ordered on the context's launch stream."""
+        import contextlib
+        import torch
+        if self._torch_stream is None:
+            return contextlib.nullcontext()
+        return torch.cuda.stream(self._torch_stream)
 
     # ---- direct NVLink transport (torch symmetric memory): peer stores + stream signals, no NCCL call per tick ----
     def _setup_p2p(self, nbytes: int, dev) -> None:
@@ -207,8 +276,9 @@ class StripDomain:
         if self.has_hi:
             ops.append(d.P2POp(d.isend, self.send_hi, self.rank + 1))
             ops.append(d.P2POp(d.irecv, self.recv_hi, self.rank + 1))
-        for req in d.batch_isend_irecv(ops):
-            req.wait()  # NCCL: the launch stream waits, the host does not
+        with self._on_stream():  # NCCL orders against torch's CURRENT stream: make that the context's launch stream
+            for req in d.batch_isend_irecv(ops):
+                req.wait()  # NCCL: the launch stream waits, the host does not
 
     # ---- re-balancing -------------------------------------------------------------------------------------------
     def rebalance(self) -> None:
@@ -217,9 +287,12 @@ class StripDomain:
         import torch.distributed as dist
         hist = self.ctx.dist_row_histogram(self._row0, self._nrows).astype(np.int64)
         dev = self._tensor_device if self._tensor_device is not None else torch.device("cuda", self.ctx.device)
-        t = torch.from_numpy(hist).to(dev)
-        dist.all_reduce(t)
-        self.target_cuts = cuts_from_histogram(t.cpu().numpy(), self._row0, self.world_size, self.halo_rows)
+        with self._on_stream():
+            t = torch.from_numpy(hist).to(dev)
+            dist.all_reduce(t)
+            t = t.cpu()
+        self._check_flags()
+        self.target_cuts = cuts_from_histogram(t.numpy(), self._row0, self.world_size, self.halo_rows)
 
     def _slide_cuts(self) -> None:
         """Every rank holds the whole cut list and moves it identically; no communication."""
@@ -250,6 +323,16 @@ class StripDomain:
                 self.ctx.dist_unpack(self.recv_lo, self.recv_hi)
         self.ctx.step()
         self.tick += 1
+        if self.check_every and self.world_size > 1 and self.tick % self.check_every == 0:
+            self._check_flags()
+
+    def _check_flags(self) -> None:
+        """Raise if the device has flagged a capacity overflow or a particle that outran the halo (results after such
+        a tick are wrong; the arrays themselves stay in bounds: the live count is clamped to the capacity)."""
+        st = self.status()
+        if st["overflow"] or st["too_far"]:
+            raise _lib.SandCrateError(f"strip {self.rank}: device flags {st} at tick {self.tick} (raise `slack` / "
+                                      f"`wire_capacity`, or `halo_rows` if particles move more than a halo per tick)")
 
     def step(self, n: int = 1) -> None:
         for _ in range(n):

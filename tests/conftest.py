@@ -51,3 +51,11 @@ def have_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def aggregates(pos, vel, prs):
+    """The bulk quantities the free-run drift bounds are stated on ("1000-step free run")."""
+    pos, vel, prs = np.asarray(pos), np.asarray(vel), np.asarray(prs)
+    return {"count": int(len(pos)), "com_x": float(pos[:, 0].mean()), "com_y": float(pos[:, 1].mean()),
+            "kinetic": float(0.5 * (vel ** 2).sum()), "mean_speed": float(np.sqrt((vel ** 2).sum(1)).mean()),
+            "p_mean": float(prs.mean()), "p_max": float(prs.max())}

@@ -5,7 +5,9 @@
 
 Every rank runs its strip of a dam-break scene (fp64 mode, counter noise, NCCL halo + migration exchange); rank 0
 also runs the whole scene on one GPU.  The gathered N-rank state must equal the single-GPU state bit for bit, and
-the single-GPU state must equal the oracle's.  Prints one line per check and exits non-zero on failure."""
+the single-GPU state must equal the oracle's (fp64 cases the oracle finishes in seconds).  SC_CHECK_SCALE=1 runs the
+re-cutter at scale instead: dam-break 2M, 200 ticks, re-cut every 25 ticks, mixed precision.  Prints one line per check
+and exits non-zero on failure."""
 import os
 import sys
 
@@ -31,8 +33,10 @@ def main():
     torch.cuda.set_stream(stream)
     ok = True
     transport = os.environ.get("SC_TRANSPORT", "nccl")
-    cases = ((dam_break, 200_000, 12, "f64", 0), (box_fill, 300_000, 8, "f64", 0),
-             (dam_break, 200_000, 12, "mixed", 0), (dam_break, 200_000, 16, "f64", 3))
+    cases = [(dam_break, 200_000, 12, "f64", 0), (box_fill, 300_000, 8, "f64", 0),
+             (dam_break, 200_000, 12, "mixed", 0), (dam_break, 200_000, 16, "f64", 3)]
+    if os.environ.get("SC_CHECK_SCALE"):  # the re-cutter at the size it was built for
+        cases = [(dam_break, 2_000_000, 200, "mixed", 25), (dam_break, 200_000, 12, "f64", 0)]
     only = os.environ.get("SC_CHECK_ONLY")  # developer aid: run some of the cases, by index ("2,3")
     if only is not None:
         cases = tuple(cases[int(k)] for k in only.split(","))
@@ -73,11 +77,27 @@ def main():
                     bad = np.nonzero(np.any(gp != sp, 1) | np.any(gv != sv, 1))[0]
                     print(f"[mgpu]   {len(bad)} particles differ, max |dpos| {np.abs(gp - sp).max():.3e}, "
                           f"max |dvel| {np.abs(gv - sv).max():.3e}", flush=True)
+            vs_oracle = ""
+            if precision == "f64" and n <= 300_000:  # the single-GPU state against the oracle, bit for bit
+                from oracle import oracle as O
+                c = world_cfg.coefficients
+                cv = np.array([c["dt"], c["particle_radius"], c["wall_collision_decay"], c["pressure_amplifier"],
+                               c["ignored_pressure"], c["collider_noise_level"], c["viscosity"], c["surface_smoothing"],
+                               c["target_pressure"], c["gravity"][0], c["gravity"][1]])
+                seg = np.array(world_cfg.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+                rp, rv = pos.copy(), vel.copy()
+                for tick in range(ticks):
+                    out = O.step(cv, rp, rv, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(5, tick),
+                                 want_all=False)
+                    rp, rv = out["pos_out"], out["vel_out"]
+                exact = np.array_equal(sp, rp) and np.array_equal(sv, rv)
+                vs_oracle = f"; single GPU == oracle after {ticks} ticks: {exact}"
+                same = same and exact
             flags = any(s["overflow"] or s["too_far"] for _, s in moved_all)
             print(f"[mgpu] transport={transport} {maker.__name__} n={n} ticks={ticks} {precision} ranks={world}: "
                   f"bit-identical to single GPU = {same}; migrated = {[m for m, _ in moved_all]}; "
                   f"local = {[s['n_local'] for _, s in moved_all]}; flags = {flags}; "
-                  f"rebalance_every = {rebalance}, cuts moved = {dom.cuts != cuts0}", flush=True)
+                  f"rebalance_every = {rebalance}, cuts moved = {dom.cuts != cuts0}{vs_oracle}", flush=True)
             ok = ok and same and not flags and sum(m for m, _ in moved_all) > 0
             single.close()
         dom.close()
