@@ -212,7 +212,7 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
     g.nrows = (int)nrows;
     g.ncols = (int)ncols;
     g.ncells = (uint32_t)(nrows * ncols);
-    const size_t need = (size_t)g.ncells + 2;
+    const size_t need = (size_t)g.ncells + 8;  // + the live count at [ncells]; bulk copies read whole 16-byte groups
     if (need > ctx->cell_cap) {
         if (ctx->cell_start) CK(cudaFree(ctx->cell_start));
         CKR(dev_alloc(ctx, &ctx->cell_start, need));
@@ -295,7 +295,8 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     { const char *e_ = getenv("SC_PAIR_MODE"); if (e_ && e_[0] >= '0' && e_[0] <= '1') c->pair_mode = e_[0] - '0'; }
     if (stream) c->stream = (cudaStream_t)stream;
     else { cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking); c->own_stream = true; }
-    const size_t n = (size_t)capacity, rs = real_size(c);
+    // + 16: the tiled kernels bulk-copy windows whose ends are rounded up to 16-byte groups
+    const size_t n = (size_t)capacity + 16, rs = real_size(c);
     int rc = 0;
     rc |= dev_alloc(c, &c->pos_cur, n); rc |= dev_alloc(c, &c->pos_srt, n);
     rc |= dev_alloc(c, (char **)&c->vel_cur, n * 2 * rs); rc |= dev_alloc(c, (char **)&c->vel_srt, n * 2 * rs);
@@ -710,6 +711,20 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
     return 0;
 }
 
+// mixed precision with device-side noise: K5 on the same blocks and windows as K4 (sc_tile.cuh)
+static int launch_force_tile(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n) {
+    if (ctx->monitor_on) CK(cudaMemsetAsync(ctx->monitor, 0, sizeof(double) * 8, ctx->stream));
+    ProfScope ps(ctx, SLOT_FORCE);
+    auto go = [&](auto kernel) {
+        return launch_pdl(kernel, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, n_ptr, dp,
+                          ctx->walls, ctx->blk_desc, ctx->pos_srt, (const float2 *)ctx->vel_srt, (const uint2 *)ctx->pair_n,
+                          ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt,
+                          ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->monitor);
+    };
+    CK(ctx->monitor_on ? go(k_force_tile<true>) : go(k_force_tile<false>));
+    return 0;
+}
+
 // mixed precision with device-side noise: K4 stages the block's neighborhood in shared memory (sc_tile.cuh)
 static int launch_density_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, int64_t n) {
     auto go = [&](auto kernel) {
@@ -747,7 +762,7 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
                 ProfScope ps(ctx, SLOT_DENSITY);
                 CKR(launch_density_tile(ctx, g, dp, n));
             }
-            CKR(launch_force<float>(ctx, dp, n_ptr, n));
+            CKR(launch_force_tile(ctx, dp, n_ptr, n));
         }
     }
     ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
@@ -1093,14 +1108,11 @@ extern "C" double sc_debug_rerun(sc_ctx *ctx, int which, int reps) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     float total = 0;
     for (int r = 0; r < reps; ++r) {
-        if (which == 4 || which == 24) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
+        if (which == 4) cudaMemsetAsync(&ctx->cnt->pair_cursor, 0, 4, ctx->stream);
         cudaEventRecord(e0, ctx->stream);
         const bool tiled = ctx->pair_mode != 0 && dp.noise_mode != SC_NOISE_HOST;
-        if (which == 24) {
-            launch_pdl(k_density_tile<SC_NOISE_COUNTER, 2>, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, ctx->cnt,
-                       ctx->grid, dp, ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt,
-                       (uint2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
-        } else if (which == 4) { if (tiled) launch_density_tile(ctx, ctx->grid, dp, n); else launch_density<float>(ctx, ctx->grid, dp, nullptr, n); }
+        if (which == 4) { if (tiled) launch_density_tile(ctx, ctx->grid, dp, n); else launch_density<float>(ctx, ctx->grid, dp, nullptr, n); }
+        else if (tiled) launch_force_tile(ctx, dp, ctx->cell_start + ctx->grid.ncells, n);
         else launch_force<float>(ctx, dp, ctx->cell_start + ctx->grid.ncells, n);
         cudaEventRecord(e1, ctx->stream);
         cudaEventSynchronize(e1);

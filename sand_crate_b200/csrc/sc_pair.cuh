@@ -166,11 +166,39 @@ __device__ __forceinline__ PairGeom<float> pair_geom_f32(const DevParams &P, flo
     return g;
 }
 
-// The record K4 hands to K5 for each directed pair (i <- j): the neighbor's sorted index and the unit vector.
-//   fp64 mode : two arrays (u32 index, double2 vector) - exact.
-//   mixed mode: ONE 8-byte word per pair: index + the vector as two signed 16-bit fractions (|error| <= 1.6e-5 per
-//               component; a pair moves a particle by ~1e-3 of its speed per tick, so this is ~1e-8 relative per tick,
-//               three orders below the mode's 1e-5 tolerance).  One store in K4, one load in K5, 8 instead of 12 bytes.
+__device__ __forceinline__ float sqrt_ftz(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The record K4 hands to K5 for each directed pair (i <- j) in mixed mode: ONE 8-byte word.
+//   .x  the SMALLER-magnitude component m of the unit vector n_ij, as a full fp32
+//   .y  bits 0..27  the neighbor's index L in the block's frame (staged block: position in W0 | W1 | W2; pass-through
+//                   block: sorted index) - K4 and K5 cut the sorted set into the same blocks and windows, so K5 reads
+//                   its neighbor's (p, s, v) from shared memory at L with no translation
+//       bit 28      which component m is (0: n.x, 1: n.y)
+//       bit 29      sign of the other component, whose magnitude K5 restores as sqrt(1 - m^2) (>= 0.707: well conditioned)
+// The vector K5 sees is good to ~1e-7 (fp32 grade).  Round 1 packed it as two signed 16-bit fractions (1.5e-5 per
+// component): that was 250x coarser than the arithmetic around it and showed in the per-tick velocity INCREMENT.
+__device__ __forceinline__ uint2 pair_encode(uint32_t L, float nx, float ny) {
+    const bool y_small = fabsf(ny) < fabsf(nx);
+    const float m = y_small ? ny : nx, big = y_small ? nx : ny;
+    return make_uint2(__float_as_uint(m), L | (y_small ? 0x10000000u : 0u) | ((__float_as_uint(big) >> 2) & 0x20000000u));
+}
+__device__ __forceinline__ void pair_decode(uint2 r, uint32_t &L, float &nx, float &ny) {
+    const float m = __uint_as_float(r.x);
+    float big = sqrt_ftz(fmaf(-m, m, 1.0f));
+    big = __uint_as_float(__float_as_uint(big) | ((r.y << 2) & 0x80000000u));
+    const bool y_small = (r.y & 0x10000000u) != 0u;
+    nx = y_small ? big : m;
+    ny = y_small ? m : big;
+    L = r.y & SC_IDX_MASK;
+}
+
+// fp64 mode keeps two exact arrays (u32 index, double2 vector); mixed mode uses the 8-byte record above, whose index
+// field holds the SORTED index in the untiled kernels of this file.
 template <typename Real> struct PairIO;
 template <> struct PairIO<double> {
     static __device__ __forceinline__ void store(uint32_t *pj, void *pn, size_t i, uint32_t j, double nx, double ny) {
@@ -187,19 +215,14 @@ template <> struct PairIO<double> {
 };
 template <> struct PairIO<float> {
     static __device__ __forceinline__ void store(uint32_t *, void *pn, size_t i, uint32_t j, float nx, float ny) {
-        const int ix = __float2int_rn(fminf(fmaxf(nx, -1.0f), 1.0f) * 32767.0f);
-        const int iy = __float2int_rn(fminf(fmaxf(ny, -1.0f), 1.0f) * 32767.0f);
-        reinterpret_cast<uint2 *>(pn)[i] = make_uint2(j, ((uint32_t)ix & 0xFFFFu) | ((uint32_t)iy << 16));
+        reinterpret_cast<uint2 *>(pn)[i] = pair_encode(j, nx, ny);
     }
     static __device__ __forceinline__ uint32_t load_index(const uint32_t *, const void *pn, size_t i) {
-        return reinterpret_cast<const uint2 *>(pn)[i].x;
+        return reinterpret_cast<const uint2 *>(pn)[i].y & SC_IDX_MASK;
     }
     static __device__ __forceinline__ void load(const uint32_t *, const void *pn, size_t i, uint32_t &j, float &nx,
                                                 float &ny) {
-        const uint2 r = reinterpret_cast<const uint2 *>(pn)[i];
-        j = r.x;
-        nx = (float)(short)(r.y & 0xFFFFu) * (1.0f / 32767.0f);
-        ny = (float)((int)r.y >> 16) * (1.0f / 32767.0f);
+        pair_decode(reinterpret_cast<const uint2 *>(pn)[i], j, nx, ny);
     }
 };
 
@@ -477,7 +500,7 @@ k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W
     Real tx = 0, ty = 0;  // F3 sum
     Real qx = 0, qy = 0;  // F5 sum
     Real sum_vx = 0, sum_vy = 0;  // fp32 mode: sum of neighbor velocities
-    // batches of 4 pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
+    // batches of SC_K5_BATCH pairs: index loads, then the dependent gathers, then the arithmetic in list order - the loop is
     // latency bound (two dependent L2 round trips per pair), so the loads of a batch are issued back to back
     for (int k0 = 0; k0 < K; k0 += SC_K5_BATCH) {
         uint32_t jj[SC_K5_BATCH];

@@ -50,8 +50,10 @@ struct __align__(16) BlockDesc {
 };
 
 struct TileWindows {
-    uint32_t base[3];  // first sorted index of W0, W1, W2
+    uint32_t base[3];  // first STAGED sorted index of W0, W1, W2: the window's first index rounded down to even, so that
+                       // 8-byte arrays (velocities) start 16-byte aligned, which the bulk copy needs
     uint32_t off[3];   // first local index of W0, W1, W2 (staged) / = base (pass-through)
+    uint32_t cnt[3];   // staged particles per window (even)
     uint32_t total;    // staged particles
     uint32_t c_lo, ncw;  // first cell of the block, cells per row slice (c_lo - 1 .. c_hi + 2)
     bool staged, cells_staged;
@@ -60,20 +62,53 @@ struct TileWindows {
 __device__ __forceinline__ TileWindows tile_windows(const BlockDesc *desc) {
     const uint4 lo = reinterpret_cast<const uint4 *>(desc)[0], hi = reinterpret_cast<const uint4 *>(desc)[1];
     TileWindows w;
-    w.base[0] = lo.x; w.base[1] = lo.y; w.base[2] = lo.z; w.c_lo = lo.w;
-    const uint32_t n0 = hi.x - lo.x, n1 = hi.y - lo.y, n2 = hi.z - lo.z;
-    w.total = n0 + n1 + n2;
+    w.base[0] = lo.x & ~1u; w.base[1] = lo.y & ~1u; w.base[2] = lo.z & ~1u; w.c_lo = lo.w;
+    w.cnt[0] = (hi.x - w.base[0] + 1u) & ~1u; w.cnt[1] = (hi.y - w.base[1] + 1u) & ~1u; w.cnt[2] = (hi.z - w.base[2] + 1u) & ~1u;
+    w.total = w.cnt[0] + w.cnt[1] + w.cnt[2];
     w.ncw = hi.w - lo.w + 4u;
     w.staged = w.total <= SC_TILE_CAP;
     w.cells_staged = w.staged && w.ncw <= SC_TILE_CELLS;
-    if (w.staged) { w.off[0] = 0u; w.off[1] = n0; w.off[2] = n0 + n1; }
+    if (w.staged) { w.off[0] = 0u; w.off[1] = w.cnt[0]; w.off[2] = w.cnt[0] + w.cnt[1]; }
     else { w.off[0] = w.base[0]; w.off[1] = w.base[1]; w.off[2] = w.base[2]; }
     return w;
 }
 
-// sorted index of the staged particle at local index t (used only while staging)
-__device__ __forceinline__ uint32_t tile_source(const TileWindows &w, uint32_t t) {
-    return t < w.off[1] ? w.base[0] + t : (t < w.off[2] ? w.base[1] + (t - w.off[1]) : w.base[2] + (t - w.off[2]));
+// ---- bulk copies (TMA engine, no tensor map): global -> shared, completion counted in bytes on an mbarrier ----------
+// One elected thread arms the barrier with the byte total and issues the copies; every thread then waits on the
+// barrier's phase.  No thread spends an instruction on moving the data, no registers hold it in flight, and the wait
+// replaces the __syncthreads of a load/store staging loop.  Source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// the three windows of a `stride`-byte-per-particle array into shared memory at `dst` (W0 | W1 | W2); returns bytes
+__device__ __forceinline__ uint32_t stage_windows(const TileWindows &w, const void *src, uint32_t stride, uint32_t dst,
+                                                  uint32_t bar) {
+    const char *g = reinterpret_cast<const char *>(src);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+        if (w.cnt[q]) bulk_g2s(dst + w.off[q] * stride, g + (size_t)w.base[q] * stride, w.cnt[q] * stride, bar);
+    return w.total * stride;
 }
 
 // accessors: shared memory by 32-bit shared address (keeps the address arithmetic to one instruction), or global
@@ -95,8 +130,6 @@ template <typename T> struct GmemAcc {
     const T *p;
     __device__ __forceinline__ T get(uint32_t L) const { return p[L]; }
 };
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // per-thread neighbor list, one column per thread; 16-bit entries when the indices are local (11 bits + row code)
 template <typename E, int kShift> struct TileList {
     E *col;
@@ -112,11 +145,10 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
 // ------------------------------------------------------------------------------------------------------------
 // K4 body for one particle.  s = sorted index; b[] = the six boundaries of its four candidate ranges as LOCAL
 // indices (m0, m3 | n0, n3 | p0, p3 of collect_neighbors, shifted into the staged windows).  List order = reference
-// list order.  The pair records carry SORTED indices (K5 gathers from global memory).
+// list order.
 template <int kNoise, class Acc, class List>
 __device__ __forceinline__ void density_particle(const Acc &A, List lst, const TileWindows &w, bool live, uint32_t s,
                                                  const uint32_t (&b)[6], const Grid &g, const DevParams &P,
@@ -198,10 +230,7 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         const float nx = rx * inv, ny = ry * inv;
         const float cl = __saturatef((q * inv) * inv_d);  // np.clip(dist / d, 0, 1), crate.py:270
         const float wgt = 1.0f - cl;
-        // one 8-byte record per directed pair: neighbor index + the unit vector as two signed 16-bit fractions
-        const int ix = __float2int_rn(nx * 32767.0f), iy = __float2int_rn(ny * 32767.0f);
-        const uint32_t jrec = L - (code == 1u ? d0 : (code == 2u ? d1 : d2));
-        out[k] = make_uint2(jrec, __byte_perm((uint32_t)ix, (uint32_t)iy, 0x5410));
+        out[k] = pair_encode(L, nx, ny);
         psum += wgt;
         const float c = cl * wgt;  // (1 - w) w, crate.py:340
         ax = fmaf(c, nx, ax);
@@ -217,12 +246,13 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
     ps_out[s] = o;
 }
 
-#define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4 + SC_MAX_NEIGHBORS * SC_TILE * 2)
+#define SC_TILE_CELL_SLOTS (SC_TILE_CELLS + 8)  // a staged row slice starts at a multiple of 4 cells: up to 3 + 3 extra
+#define SC_TILE_SMEM_K4 (SC_TILE_CAP * 16 + 3 * SC_TILE_CELL_SLOTS * 4 + SC_MAX_NEIGHBORS * SC_TILE * 2)
 
-template <int kNoise, int kRepeat = 1>
 #ifndef SC_TILE_RESIDENT
 #define SC_TILE_RESIDENT 1536  // threads per SM the register allocation is held to (1536 = 40 registers)
 #endif
+template <int kNoise>
 __global__ void __launch_bounds__(SC_TILE, SC_TILE_RESIDENT / SC_TILE)
 k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
                const BlockDesc *desc, const double2 *pos,
@@ -230,8 +260,9 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
                uint2 *pair_rec, uint32_t *pair_off, uint8_t *pair_cnt,
                PS<float> *ps_out) {
     pdl_enter();
-    // staged: [records 20 KB | cell boundaries 5.25 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
-    __shared__ __align__(16) unsigned char s_raw[SC_TILE_SMEM_K4];
+    // staged: [records 20 KB | cell boundaries 4.7 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
+    __shared__ __align__(128) unsigned char s_raw[SC_TILE_SMEM_K4];
+    __shared__ __align__(8) unsigned long long s_bar;
     static_assert(SC_TILE_SMEM_K4 >= SC_MAX_NEIGHBORS * SC_TILE * 4, "pass-through lists must fit");
     const uint32_t b0 = blockIdx.x * SC_TILE;
     const uint32_t s = b0 + threadIdx.x;
@@ -246,36 +277,45 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
     if (w.staged) {
         SearchRec *s_rec = reinterpret_cast<SearchRec *>(s_raw);
         uint32_t *s_cs = reinterpret_cast<uint32_t *>(s_raw + SC_TILE_CAP * 16);
-        uint16_t *s_list = reinterpret_cast<uint16_t *>(s_raw + SC_TILE_CAP * 16 + 3 * SC_TILE_CELLS * 4);
-        // second round: the three windows and (unless the block wraps around a row end) its cell boundaries, stored
-        // as local indices
-        for (uint32_t t = threadIdx.x; t < w.total; t += SC_TILE) s_rec[t] = rec[tile_source(w, t)];
-        const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
-        if (w.cells_staged) {
-            const uint32_t *src = cell_start + w.c_lo - 1u;
-            for (uint32_t t = threadIdx.x; t < w.ncw; t += SC_TILE) {
-                s_cs[t] = src[t] + d0;
-                s_cs[SC_TILE_CELLS + t] = src[nc + t] + d1;
-                s_cs[2 * SC_TILE_CELLS + t] = (src - nc)[t] + d2;
+        uint16_t *s_list = reinterpret_cast<uint16_t *>(s_raw + SC_TILE_CAP * 16 + 3 * SC_TILE_CELL_SLOTS * 4);
+        const uint32_t bar = smem_addr(&s_bar);
+        // second round: the three windows and (unless the block wraps around a row end) its three slices of the cell
+        // boundaries, by bulk copy.  A slice starts at the multiple of 4 cells at or below c_lo - 1 (16-byte alignment).
+        const uint32_t i0 = w.c_lo - 1u, i1 = i0 + nc, i2 = i0 - nc;
+        const uint32_t a0 = i0 & ~3u, a1 = i1 & ~3u, a2 = i2 & ~3u;
+        if (threadIdx.x == 0) mbar_init(bar, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t bytes = w.total * 16u;
+            const uint32_t n0 = (i0 - a0 + w.ncw + 3u) & ~3u, n1 = (i1 - a1 + w.ncw + 3u) & ~3u, n2 = (i2 - a2 + w.ncw + 3u) & ~3u;
+            if (w.cells_staged) bytes += (n0 + n1 + n2) * 4u;
+            mbar_expect_tx(bar, bytes);
+            stage_windows(w, rec, 16u, smem_addr(s_rec), bar);
+            if (w.cells_staged) {
+                const uint32_t cs = smem_addr(s_cs);
+                bulk_g2s(cs, cell_start + a0, n0 * 4u, bar);
+                bulk_g2s(cs + SC_TILE_CELL_SLOTS * 4u, cell_start + a1, n1 * 4u, bar);
+                bulk_g2s(cs + 2u * SC_TILE_CELL_SLOTS * 4u, cell_start + a2, n2 * 4u, bar);
             }
-        } else if (live) {
+        }
+        const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
+        if (!w.cells_staged && live) {
             const uint32_t *cs0 = cell_start + c - 1u;
             b[0] = cs0[0] + d0; b[1] = cs0[3] + d0;
             b[2] = cs0[nc] + d1; b[3] = cs0[nc + 3u] + d1;
             b[4] = (cs0 - nc)[0] + d2; b[5] = (cs0 - nc)[3] + d2;
         }
-        __syncthreads();
+        mbar_wait(bar, 0u);
         if (w.cells_staged) {
             const uint32_t q = c - w.c_lo;
-            b[0] = s_cs[q]; b[1] = s_cs[q + 3u];
-            b[2] = s_cs[SC_TILE_CELLS + q]; b[3] = s_cs[SC_TILE_CELLS + q + 3u];
-            b[4] = s_cs[2 * SC_TILE_CELLS + q]; b[5] = s_cs[2 * SC_TILE_CELLS + q + 3u];
+            const uint32_t *r0 = s_cs + (i0 - a0) + q, *r1 = s_cs + SC_TILE_CELL_SLOTS + (i1 - a1) + q,
+                           *r2 = s_cs + 2 * SC_TILE_CELL_SLOTS + (i2 - a2) + q;
+            b[0] = r0[0] + d0; b[1] = r0[3] + d0;
+            b[2] = r1[0] + d1; b[3] = r1[3] + d1;
+            b[4] = r2[0] + d2; b[5] = r2[3] + d2;
         }
-#pragma unroll 1
-        for (int rep = 0; rep < kRepeat; ++rep)  // kRepeat > 1: developer timing aid (cost of a pass without its prologue)
-        density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr(s_rec)},
-                                             TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live, s, b, g, P, cnt, pos,
-                                             pair_rec, pair_off, pair_cnt, ps_out);
+        density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr(s_rec)}, TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live,
+                                 s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
     } else {
         if (threadIdx.x == 0) atomicAdd(&cnt->n_untiled, 1u);  // rare; lets a test prove this path ran
         if (live) {
@@ -285,9 +325,93 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
             b[4] = (cs0 - nc)[0]; b[5] = (cs0 - nc)[3];
         }
         density_particle<kNoise>(GmemAcc<SearchRec>{rec},
-                                             TileList<uint32_t, 28>{reinterpret_cast<uint32_t *>(s_raw) + threadIdx.x}, w,
-                                             live, s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
+                                 TileList<uint32_t, 28>{reinterpret_cast<uint32_t *>(s_raw) + threadIdx.x}, w,
+                                 live, s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5 (mixed mode, device noise): the same blocks and windows as K4.  The neighbors' pressure / surface normal
+// (16 bytes) and velocity (8 bytes) are bulk-copied into shared memory while the threads fetch their own record
+// offsets; the pair loop then reads ld.shared.v4 / .v2 at the local index the pair record carries, instead of two
+// dependent global gathers per pair (which made the untiled kernel latency bound at 38 % occupancy).
+// Round 1 built this with a load/store staging loop and measured it SLOWER than gathering (60 vs 46 us): the loop's
+// instructions, its registers in flight and its barrier cost more than the gathers saved.  The bulk copy has none of
+// the three.
+template <bool kMonitor>
+__global__ void __launch_bounds__(SC_TILE, 4)
+k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W, const BlockDesc *desc,
+             const double2 *pos, const float2 *vel, const uint2 *pair_rec, const uint32_t *pair_off,
+             const uint8_t *pair_cnt, const PS<float> *ps_in, const uint32_t *wall_bits, const uint32_t *wall_slot,
+             const double2 *wall_pre, double2 *pos_out, float2 *vel_out, double *monitor) {
+    pdl_enter();
+    __shared__ __align__(128) float4 s_ps[SC_TILE_CAP];
+    __shared__ __align__(128) float2 s_vel[SC_TILE_CAP];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t b0 = blockIdx.x * SC_TILE;
+    const uint32_t n = *n_ptr;
+    if (b0 >= n) return;
+    const uint32_t s = b0 + threadIdx.x;
+    const bool live = s < n;
+    const TileWindows w = tile_windows(desc + blockIdx.x);
+    const uint32_t bar = smem_addr(&s_bar);
+    if (w.staged) {
+        if (threadIdx.x == 0) mbar_init(bar, 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, w.total * 24u);
+            stage_windows(w, ps_in, 16u, smem_addr(s_ps), bar);
+            stage_windows(w, vel, 8u, smem_addr(s_vel), bar);
+        }
+    }
+    // own record, straight from global memory while the copies fly
+    PS<float> me;
+    uint32_t off = 0;
+    int K = 0;
+    uint2 rnext = make_uint2(0u, 0u);
+    if (live) {
+        me = ps_in[s];
+        off = pair_off[s];
+        K = pair_cnt[s];
+        if (K) rnext = pair_rec[off];
+    }
+    if (w.staged) mbar_wait(bar, 0u);
+    if (!live) return;
+    const float p_i = me.p;
+    const float smooth = (float)P.smooth, two_target = (float)(2 * P.target);
+    float tx = 0, ty = 0;         // F3 sum
+    float qx = 0, qy = 0;         // F5 sum
+    float sum_vx = 0, sum_vy = 0;  // sum of neighbor velocities (F6)
+    const SmemAcc<float4> Aps{smem_addr(s_ps)};
+    const SmemAcc<float2> Avel{smem_addr(s_vel)};
+    for (int k = 0; k < K; ++k) {
+        const uint2 r = rnext;
+        if (k + 1 < K) rnext = pair_rec[off + k + 1];  // the next record is in flight while this pair is evaluated
+        uint32_t L;
+        float nx, ny;
+        pair_decode(r, L, nx, ny);
+        float4 nb;
+        float2 vj;
+        if (w.staged) { nb = Aps.get(L); vj = Avel.get(L); }
+        else { const PS<float> g_ = ps_in[L]; nb = make_float4(g_.p, g_.sx, g_.sy, 0.0f); vj = vel[L]; }
+        // F3 pass 2, crate.py:347-353
+        const float ddx = me.sx - nb.y, ddy = me.sy - nb.z;
+        const float align = (ddx * nx + ddy * ny) * smooth;
+        const float fix = nb.x + p_i - two_target;
+        const float cc = align + fix;
+        const float ex = cc * nx, ey = cc * ny;
+        // F5, crate.py:301-306
+        const float ps_ = p_i + nb.x;
+        const float fx = nx * ps_, fy = ny * ps_;
+        if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
+        else { tx += ex; ty += ey; qx += fx; qy += fy; }
+        sum_vx += vj.x; sum_vy += vj.y;
+    }
+    force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
+                                monitor, n_ptr, [&](float vx, float vy, float &ax, float &ay) {
+        ax = sum_vx - (float)K * vx;
+        ay = sum_vy - (float)K * vy;
+    });
 }
 
 }  // namespace sc
