@@ -184,6 +184,11 @@ int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_recv_lo_dev, v
                  const void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value);
 int sc_dist_unpack_flagged(sc_ctx *ctx, const void *recv_lo_dev, const void *flag_lo_dev, const void *recv_hi_dev,
                            const void *flag_hi_dev, uint32_t value);
+/* sc_dist_pack and sc_dist_push as ONE kernel: the records are written straight into the neighbors' receive buffers
+ * as they are produced (peer stores over NVLink), the last block to finish publishes the counts and raises the flags.
+ * send_*_dev are still needed (their headers hold the record counters and the sticky overflow / too_far marks). */
+int sc_dist_pack_push(sc_ctx *ctx, void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev, void *send_hi_dev,
+                      void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value);
 /* owned particles of this rank, in arbitrary order; uid[i] identifies row i.  Synchronises. */
 int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int64_t cap, int64_t *n);
 /* device-side flags since creation: capacity overflow, a particle that crossed a whole halo in one tick; the

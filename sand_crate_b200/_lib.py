@@ -76,6 +76,7 @@ SIGNATURES = {
     "sc_dist_unpack": (C.c_int, [_ctx, C.c_void_p, C.c_void_p]),
     "sc_dist_push": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_unpack_flagged": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
+    "sc_dist_pack_push": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_get_owned": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64, _lp]),
     "sc_dist_status": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
     "sc_dist_row_histogram": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
@@ -348,6 +349,12 @@ class Context:
         lo, hi = lo or (None, None, None), hi or (None, None, None)
         self._ck(self._L.sc_dist_push(self._h, *[self._devptr(x) for x in lo], *[self._devptr(x) for x in hi],
                                       C.c_uint32(value)))
+
+    def dist_pack_push(self, lo, hi, value):
+        """pack + push fused.  lo / hi: None or (send buffer, peer receive address, peer flag address)."""
+        lo, hi = lo or (None, None, None), hi or (None, None, None)
+        self._ck(self._L.sc_dist_pack_push(self._h, *[self._devptr(x) for x in lo], *[self._devptr(x) for x in hi],
+                                           C.c_uint32(value)))
 
     def dist_unpack_flagged(self, lo, hi, value):
         """lo / hi: None or (receive address, flag address)."""

@@ -56,11 +56,18 @@ struct sc_ctx {
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
     uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
-    uint32_t *cell_start = nullptr; size_t cell_cap = 0;
-    unsigned long long *bsum = nullptr; size_t bsum_cap = 0;  // scan tile descriptors; [bsum_cap - 1] = ticket
+    // The cell grid and the wall bitmaps are double buffered by tick parity: a tick's force kernel clears the OTHER set
+    // for the next tick (end_of_tick, sc_common.cuh), so a tick does not open with a clearing launch.  cell_start /
+    // wall_bits_* always point at the set of the last search (the taps read them).
+    uint32_t *cell_bufs[2] = {nullptr, nullptr}, *cell_start = nullptr; size_t cell_cap = 0;
+    int par = 0;
+    bool next_clean = false;  // the other set has been cleared by the last force kernel
+    unsigned long long *bsum = nullptr; size_t bsum_cap = 0;    // cell scan: tile descriptors, [0] = ticket
+    unsigned long long *bsum2 = nullptr; size_t bsum2_cap = 0;  // the same for every other scan (readback maps)
     void *ps = nullptr;               // PS<Real>[cap]: pressure + surface normal of the sorted set
     uint32_t *pair_j = nullptr; void *pair_n = nullptr;  // [cap * SC_MAX_NEIGHBORS], written by K4, read by K5
     uint32_t *pair_off = nullptr; uint8_t *pair_cnt = nullptr;
+    uint32_t *wbits_cur[2] = {nullptr, nullptr}, *wbits_srt[2] = {nullptr, nullptr};
     uint32_t *wall_bits_cur = nullptr, *wall_bits_srt = nullptr, *wall_slot_cur = nullptr, *wall_slot_srt = nullptr;
     double2 *wall_pre = nullptr;
     Counters *cnt = nullptr;
@@ -73,6 +80,7 @@ struct sc_ctx {
     bool n_exact = true;
     bool in_step = false;     // between sc_step_begin and sc_step_finish
     bool srt_valid = false;   // *_srt arrays hold the last tick's search state
+    bool rows_valid = false;  // pos_cur / uid_cur are still in the order of the last search (cell rows ascending)
     bool lists_valid = false, rank_valid = false;
     bool carry_count = false; // the device count must be refreshed from the previous tick's scan total
     int pair_mode = 1;  // mixed mode with device noise: 1 = tiled K4 (sc_tile.cuh), 0 = the untiled K4 of sc_pair.cuh
@@ -214,10 +222,14 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
     g.ncells = (uint32_t)(nrows * ncols);
     const size_t need = (size_t)g.ncells + 8;  // + the live count at [ncells]; bulk copies read whole 16-byte groups
     if (need > ctx->cell_cap) {
-        if (ctx->cell_start) CK(cudaFree(ctx->cell_start));
-        CKR(dev_alloc(ctx, &ctx->cell_start, need));
+        for (int q = 0; q < 2; ++q) {
+            if (ctx->cell_bufs[q]) CK(cudaFree(ctx->cell_bufs[q]));
+            CKR(dev_alloc(ctx, &ctx->cell_bufs[q], need));
+        }
         ctx->cell_cap = need;
     }
+    ctx->cell_start = ctx->cell_bufs[ctx->par];
+    ctx->next_clean = false;  // a new grid: the next tick clears it itself
     const size_t nb = (size_t)(g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
     const size_t nb2 = (size_t)(ctx->cap + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
     const size_t needb = nb > nb2 ? nb : nb2;
@@ -250,7 +262,7 @@ static int world_grid(sc_ctx *ctx) {
         if (ctx->dist.has_hi && ctx->dist.row_hi + margin < rhi) rhi = (int)(ctx->dist.row_hi + margin);
     }
     CKR(setup_grid(ctx, d, rlo, rhi, lo, hi));
-    ctx->srt_valid = false;
+    ctx->srt_valid = false; ctx->rows_valid = false;
     return 0;
 }
 
@@ -309,10 +321,15 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
         rc |= dev_alloc(c, &c->blk_desc, (n + SC_TILE - 1) / SC_TILE + 1);
     }
     rc |= dev_alloc(c, (char **)&c->ps, n * 4 * rs);
-    rc |= dev_alloc(c, &c->pair_j, n * SC_MAX_NEIGHBORS);
-    rc |= dev_alloc(c, (char **)&c->pair_n, n * SC_MAX_NEIGHBORS * 2 * rs);
+    // pair records: the untiled kernels bump-allocate; the tiled kernels give every block of SC_TILE sorted particles its
+    // own slot-major region of SC_TILE x 20 records, so the buffer holds whole blocks
+    const size_t npair = ((n + SC_TILE - 1) / SC_TILE) * SC_TILE * SC_MAX_NEIGHBORS;
+    rc |= dev_alloc(c, &c->pair_j, precision == SC_PRECISION_F64 ? npair : 1);
+    rc |= dev_alloc(c, (char **)&c->pair_n, npair * 2 * rs);
+    if (!rc) cudaMemsetAsync(c->pair_n, 0, npair * 2 * rs, c->stream);  // K5 bulk-copies slots K4 may not have written
     rc |= dev_alloc(c, &c->pair_off, n); rc |= dev_alloc(c, &c->pair_cnt, n);
-    rc |= dev_alloc(c, &c->wall_bits_cur, n / 32 + 1); rc |= dev_alloc(c, &c->wall_bits_srt, n / 32 + 1);
+    for (int q = 0; q < 2; ++q) { rc |= dev_alloc(c, &c->wbits_cur[q], n / 32 + 1); rc |= dev_alloc(c, &c->wbits_srt[q], n / 32 + 1); }
+    c->wall_bits_cur = c->wbits_cur[0]; c->wall_bits_srt = c->wbits_srt[0];
     rc |= dev_alloc(c, &c->wall_slot_cur, n); rc |= dev_alloc(c, &c->wall_slot_srt, n);
     rc |= dev_alloc(c, &c->wall_pre, n);
     rc |= dev_alloc(c, &c->cnt, 1);
@@ -330,8 +347,8 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_start, c->bsum, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
-                    c->wall_bits_cur, c->wall_bits_srt, c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_bufs[0], c->cell_bufs[1], c->bsum, c->bsum2, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
+                    c->wbits_cur[0], c->wbits_cur[1], c->wbits_srt[0], c->wbits_srt[1], c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy, c->monitor};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &p : c->pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
@@ -504,7 +521,7 @@ extern "C" int sc_set_state(sc_ctx *ctx, const double *pos, const double *vel, i
     if (n < 0 || n > ctx->cap) return fail(ctx, "sc_set_state: n exceeds capacity");
     if (ctx->in_step) return fail(ctx, "sc_set_state: inside a split step");
     ctx->next_uid = 0;
-    ctx->srt_valid = false; ctx->lists_valid = false;
+    ctx->srt_valid = false; ctx->lists_valid = false; ctx->rows_valid = false;
     ctx->carry_count = false;  // the count is (re)defined by the host below
     const uint32_t zero = 0;
     CK(cudaMemcpyAsync(&ctx->cnt->n, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -533,7 +550,7 @@ extern "C" int sc_append_particles(sc_ctx *ctx, const double *pos, const double 
     if (n < 0) return fail(ctx, "sc_append_particles: n < 0");
     CKR(sync_count(ctx));
     if (ctx->n_host + n > ctx->cap) return fail(ctx, "sc_append_particles: capacity exceeded");
-    ctx->srt_valid = false; ctx->lists_valid = false;
+    ctx->srt_valid = false; ctx->lists_valid = false;  // (appended rows sit behind the sorted ones: rows_valid stays)
     return upload_particles(ctx, pos, vel, ctx->n_host, n);
 }
 
@@ -564,16 +581,20 @@ extern "C" int sc_particle_count(sc_ctx *ctx, int64_t *n) {
 static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot, bool pre_cleared = false) {
     const unsigned nb = (n + SC_SCAN_TILE - 1) / SC_SCAN_TILE;
     if (nb == 0) { CK(cudaMemsetAsync(a, 0, sizeof(uint32_t), ctx->stream)); return 0; }
-    if ((size_t)nb + 2 > ctx->bsum_cap) {
+    // the cell scan's descriptors (bsum) are kept zeroed from tick to tick by the force kernel; every other scan uses
+    // its own set and zeroes it here
+    unsigned long long *&desc = pre_cleared ? ctx->bsum : ctx->bsum2;
+    size_t &cap = pre_cleared ? ctx->bsum_cap : ctx->bsum2_cap;
+    if ((size_t)nb + 2 > cap) {
         CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->bsum) CK(cudaFree(ctx->bsum));
-        CKR(dev_alloc(ctx, &ctx->bsum, (size_t)nb + 2));
-        ctx->bsum_cap = (size_t)nb + 2;
+        if (desc) CK(cudaFree(desc));
+        CKR(dev_alloc(ctx, &desc, (size_t)nb + 2));
+        cap = (size_t)nb + 2;
         pre_cleared = false;
     }
-    if (!pre_cleared) CK(cudaMemsetAsync(ctx->bsum, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
+    if (!pre_cleared) CK(cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * ((size_t)nb + 1), ctx->stream));
     ProfScope ps(ctx, slot);
-    CK(launch_pdl(k_scan_lookback, dim3(nb), dim3(SC_SCAN_THREADS), ctx->stream, a, n, ctx->bsum + 1, (uint32_t *)ctx->bsum));
+    CK(launch_pdl(k_scan_lookback, dim3(nb), dim3(SC_SCAN_THREADS), ctx->stream, a, n, desc + 1, (uint32_t *)desc));
     return 0;
 }
 
@@ -609,9 +630,14 @@ static int require_ready(sc_ctx *ctx, const char *who) {
 template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
     const int64_t n = ctx->n_host;
     const Grid &g = ctx->grid;
-    {
+    // this tick's buffer set: the one the previous tick's force kernel cleared
+    ctx->par ^= 1;
+    ctx->cell_start = ctx->cell_bufs[ctx->par];
+    ctx->wall_bits_cur = ctx->wbits_cur[ctx->par];
+    ctx->wall_bits_srt = ctx->wbits_srt[ctx->par];
+    if (!ctx->next_clean) {  // cold start: first tick of the context / first after the grid was rebuilt
         ProfScope ps(ctx, SLOT_CLEAR);
-        const uint32_t words = (uint32_t)(n / 32 + 1);
+        const uint32_t words = (uint32_t)(ctx->cap / 32 + 1);
         const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
         const uint32_t scan_words = (g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;  // ticket + descriptors
         CK(launch_pdl(k_begin_tick, dim3(nb), dim3(SC_BLOCK), ctx->stream, ctx->cnt, ctx->cell_start, g.ncells,
@@ -619,11 +645,12 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
                       (uint32_t)ctx->cap));
         ctx->carry_count = false;
     }
+    ctx->next_clean = false;
     if (n > 0) {
         ProfScope ps(ctx, SLOT_PREPASS);
         CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
                       ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre));
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap));
     }
     CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
@@ -631,7 +658,7 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
             ProfScope ps(ctx, SLOT_PLACE);
             CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
                           (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
-                          (const uint32_t *)ctx->cell_start, ctx->tmpidx));
+                          (const uint32_t *)ctx->cell_start, ctx->tmpidx, (uint32_t)ctx->cap));
         }
         ProfScope ps(ctx, SLOT_RANK_GATHER);
         if (ctx->precision == SC_PRECISION_F64)
@@ -693,6 +720,17 @@ static int launch_density(sc_ctx *ctx, const Grid &g, const DevParams &dp, const
     return 0;
 }
 
+// what this tick's force kernel clears for the next tick (TickDuty, sc_common.cuh)
+static TickDuty tick_duty(sc_ctx *ctx) {
+    TickDuty d;
+    const int o = ctx->par ^ 1;
+    d.cells = ctx->cell_bufs[o]; d.ncells = ctx->grid.ncells;
+    d.bits_a = ctx->wbits_cur[o]; d.bits_b = ctx->wbits_srt[o]; d.nbits = (uint32_t)(ctx->cap / 32 + 1);
+    d.scan_desc = ctx->bsum; d.scan_words = (ctx->grid.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
+    d.cnt = ctx->cnt;
+    return d;
+}
+
 template <typename Real>
 static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr, int64_t n) {
     typedef typename Vec2<Real>::type R2;
@@ -705,7 +743,7 @@ static int launch_force(sc_ctx *ctx, const DevParams &dp, const uint32_t *n_ptr,
         return launch_pdl(kernel, dim3(nb), dim3(nt), ctx->stream, n_ptr, dp, ctx->walls, ctx->pos_srt,
                           (const R2 *)ctx->vel_srt, ctx->pair_j, (const R2 *)ctx->pair_n, ctx->pair_off, ctx->pair_cnt,
                           (const PS<Real> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre,
-                          ctx->pos_cur, (R2 *)ctx->vel_cur, ctx->monitor);
+                          ctx->pos_cur, (R2 *)ctx->vel_cur, ctx->monitor, tick_duty(ctx));
     };
     CK(ctx->monitor_on ? go(k_force<Real, true>) : go(k_force<Real, false>));
     return 0;
@@ -718,8 +756,8 @@ static int launch_force_tile(sc_ctx *ctx, const DevParams &dp, const uint32_t *n
     auto go = [&](auto kernel) {
         return launch_pdl(kernel, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, n_ptr, dp,
                           ctx->walls, ctx->blk_desc, ctx->pos_srt, (const float2 *)ctx->vel_srt, (const uint2 *)ctx->pair_n,
-                          ctx->pair_off, ctx->pair_cnt, (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt,
-                          ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->monitor);
+                          ctx->pair_cnt, (const PS<float> *)ctx->ps, ctx->wall_bits_srt, ctx->wall_slot_srt,
+                          ctx->wall_pre, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->monitor, tick_duty(ctx));
     };
     CK(ctx->monitor_on ? go(k_force_tile<true>) : go(k_force_tile<false>));
     return 0;
@@ -730,7 +768,7 @@ static int launch_density_tile(sc_ctx *ctx, const Grid &g, const DevParams &dp, 
     auto go = [&](auto kernel) {
         return launch_pdl(kernel, dim3((unsigned)((n + SC_TILE - 1) / SC_TILE)), dim3(SC_TILE), ctx->stream, ctx->cnt, g, dp,
                           ctx->cell_start, ctx->blk_desc, ctx->pos_srt, ctx->rec_srt, ctx->cell_key_srt, (uint2 *)ctx->pair_n,
-                          ctx->pair_off, ctx->pair_cnt, (PS<float> *)ctx->ps);
+                          ctx->pair_cnt, (PS<float> *)ctx->ps);
     };
     CK(dp.noise_mode == SC_NOISE_COUNTER ? go(k_density_tile<SC_NOISE_COUNTER>) : go(k_density_tile<SC_NOISE_NONE>));
     return 0;
@@ -765,10 +803,12 @@ static int enqueue_forces(sc_ctx *ctx, const uint32_t *noise_off) {
             CKR(launch_force_tile(ctx, dp, n_ptr, n));
         }
     }
-    ctx->carry_count = true;  // cnt->n is refreshed lazily: by the next k_begin_tick or by sync_count
+    if (n > 0) { ctx->next_clean = true; ctx->carry_count = false; }  // the force kernel carried the count and cleared the other set
+    else ctx->carry_count = true;  // nothing ran: cnt->n is refreshed by the next cold start or by sync_count
     CK(cudaGetLastError());
     // the new state (pos_cur, vel_cur) is in this tick's sorted order, whose uids are uid_srt
     uint32_t *t = ctx->uid_cur; ctx->uid_cur = ctx->uid_srt; ctx->uid_srt = t;
+    ctx->rows_valid = n > 0;
     ctx->tick += 1;  // crate.py:127
     ctx->n_exact = false;
     return 0;
@@ -1088,10 +1128,17 @@ extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int6
 extern "C" int sc_last_pair_count(sc_ctx *ctx, int64_t *n_pairs) {
     if (!ctx || !n_pairs) return fail(ctx, "sc_last_pair_count: NULL argument");
     CK(cudaSetDevice(ctx->device));
+    if (!ctx->srt_valid) { *n_pairs = 0; return 0; }
+    CK(cudaMemsetAsync(&ctx->cnt->n_pairs, 0, sizeof(uint32_t), ctx->stream));
+    if (ctx->n_host > 0) {
+        ProfScope ps(ctx, SLOT_COUNT);
+        k_sum_pair_counts<<<blocks_for(ctx->n_host), SC_BLOCK, 0, ctx->stream>>>(ctx->cell_start + ctx->grid.ncells,
+                                                                                ctx->pair_cnt, &ctx->cnt->n_pairs);
+    }
     Counters h;
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    *n_pairs = (int64_t)h.pair_cursor;
+    *n_pairs = (int64_t)h.n_pairs;
     return 0;
 }
 
@@ -1269,10 +1316,14 @@ extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, u
     return 0;
 }
 
-extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
-    CKR(dist_ready(ctx, "sc_dist_pack"));
+// pack (and, with peer pointers, push) the boundary particles of this tick
+static int enqueue_pack(sc_ctx *ctx, const char *who, void *send_lo_dev, void *send_hi_dev, void *peer_recv_lo,
+                        void *peer_flag_lo, void *peer_recv_hi, void *peer_flag_hi, bool direct, uint32_t value) {
+    CKR(dist_ready(ctx, who));
     if ((ctx->dist.has_lo && !send_lo_dev) || (ctx->dist.has_hi && !send_hi_dev))
-        return fail(ctx, "sc_dist_pack: a neighbor exists but its send buffer is NULL");
+        return fail(ctx, std::string(who) + ": a neighbor exists but its send buffer is NULL");
+    if (direct && ((ctx->dist.has_lo && (!peer_recv_lo || !peer_flag_lo)) || (ctx->dist.has_hi && (!peer_recv_hi || !peer_flag_hi))))
+        return fail(ctx, std::string(who) + ": a neighbor exists but its peer pointers are NULL");
     WireHeader *lo = send_lo_dev ? (WireHeader *)send_lo_dev : ctx->wire_dummy;
     WireHeader *hi = send_hi_dev ? (WireHeader *)send_hi_dev : ctx->wire_dummy + 1;
     if (lo != ctx->send_lo || hi != ctx->send_hi) {  // first use of these buffers: arm them (later k_dist_unpack does)
@@ -1284,19 +1335,57 @@ extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
     const uint32_t *n_in = ctx->carry_count ? ctx->cell_start + ctx->grid.ncells : &ctx->cnt->n;
     ctx->carry_count = false;
     const int64_t n = ctx->n_host;
-    if (n > 0) {
+    const Grid &g = ctx->grid;
+    // Boundary zones in sorted-index space (see k_dist_pack).  Rows that can hold a ghost, a migrant or a halo particle:
+    // within halo of a cut, plus the rows a particle can cross in a tick (< 2) and a sliding cut can move (<= halo - 2),
+    // on either side.  Valid only while the arrays are still in the order of the last search.
+    PackRange R{nullptr, 0u, 0u};
+    int64_t launch_n = n;
+    if (ctx->rows_valid) {
+        const long long zone = 2LL * ctx->dist.halo + 4;
+        long long ra = ctx->dist.row_lo + zone - g.row_min, rb = ctx->dist.row_hi - zone - g.row_min;
+        ra = ra < 0 ? 0 : (ra > g.nrows ? g.nrows : ra);
+        rb = rb < 0 ? 0 : (rb > g.nrows ? g.nrows : rb);
+        if (!ctx->dist.has_lo) ra = 0;
+        if (!ctx->dist.has_hi) rb = g.nrows;
+        if (ra < rb) {
+            R.cell_start = ctx->cell_start;
+            R.cell_a = (uint32_t)(ra * g.ncols); R.cell_b = (uint32_t)(rb * g.ncols);
+            const int64_t zone_cap = 4LL * ctx->dist.cap;   // wire capacity is 4 (halo + 2) rows' worth: ample for two zones
+            launch_n = std::min<int64_t>(n, zone_cap);
+        }
+    }
+    PackOut plo{lo, reinterpret_cast<WireRec *>(lo + 1), nullptr, nullptr}, phi{hi, reinterpret_cast<WireRec *>(hi + 1), nullptr, nullptr};
+    if (direct) {
+        if (ctx->dist.has_lo) { plo.peer_hdr = (WireHeader *)peer_recv_lo; plo.recs = reinterpret_cast<WireRec *>(plo.peer_hdr + 1); plo.peer_flag = (uint32_t *)peer_flag_lo; }
+        if (ctx->dist.has_hi) { phi.peer_hdr = (WireHeader *)peer_recv_hi; phi.recs = reinterpret_cast<WireRec *>(phi.peer_hdr + 1); phi.peer_flag = (uint32_t *)peer_flag_hi; }
+    }
+    uint32_t *done = reinterpret_cast<uint32_t *>(ctx->wire_dummy + 3);  // "blocks done" counter of the fused kernel
+    if (launch_n > 0) {
         ProfScope ps(ctx, SLOT_DIST_PACK);
-        if (ctx->precision == SC_PRECISION_F64)
-            CK(launch_maybe_pdl(dist_pdl_mask() & 1, k_dist_pack<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const double2 *)ctx->vel_cur, ctx->uid_cur, lo, hi));
-        else
-            CK(launch_maybe_pdl(dist_pdl_mask() & 1, k_dist_pack<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                ctx->cnt, n_in, ctx->grid, ctx->dist, ctx->pos_cur, (const float2 *)ctx->vel_cur, ctx->uid_cur, lo, hi));
+        const dim3 grid(blocks_for(launch_n)), block(SC_BLOCK);
+        const bool pdl = dist_pdl_mask() & 1;
+#define SC_PACK(REAL, DIRECT)                                                                                        \
+        CK(launch_maybe_pdl(pdl, k_dist_pack<REAL, DIRECT>, grid, block, ctx->stream, ctx->cnt, n_in, g, ctx->dist, R,   \
+                            ctx->pos_cur, (const Vec2<REAL>::type *)ctx->vel_cur, ctx->uid_cur, plo, phi, done, value))
+        if (ctx->precision == SC_PRECISION_F64) { if (direct) SC_PACK(double, true); else SC_PACK(double, false); }
+        else { if (direct) SC_PACK(float, true); else SC_PACK(float, false); }
+#undef SC_PACK
     }
     CK(cudaGetLastError());
-    ctx->srt_valid = false; ctx->rank_valid = false; ctx->lists_valid = false;
+    ctx->srt_valid = false; ctx->rank_valid = false; ctx->lists_valid = false; ctx->rows_valid = false;
     ctx->n_exact = false;
     return 0;
+}
+
+extern "C" int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev) {
+    return enqueue_pack(ctx, "sc_dist_pack", send_lo_dev, send_hi_dev, nullptr, nullptr, nullptr, nullptr, false, 0u);
+}
+
+extern "C" int sc_dist_pack_push(sc_ctx *ctx, void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev,
+                                 void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value) {
+    return enqueue_pack(ctx, "sc_dist_pack_push", send_lo_dev, send_hi_dev, peer_recv_lo_dev, peer_flag_lo_dev,
+                        peer_recv_hi_dev, peer_flag_hi_dev, true, value);
 }
 
 static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, const void *recv_hi,

@@ -85,6 +85,27 @@ struct Counters {
     uint32_t n_untiled;    // blocks of the tiled K4 that ran in pass-through mode this tick (windows too large to stage)
 };
 
+// What the tick's LAST kernel (the force kernel) does for the NEXT tick, spread over its threads, so that a tick does
+// not open with a clearing launch: zero the other cell-count grid and the other pair of wall bitmaps (both are double
+// buffered by tick parity: this tick's are still being read), zero the cell scan's tile descriptors and ticket, carry
+// the live count (the scan total) into cnt->n and reset the wall side list.
+struct TickDuty {
+    uint32_t *cells; uint32_t ncells;            // next tick's cell-count grid
+    uint32_t *bits_a, *bits_b; uint32_t nbits;   // next tick's wall bitmaps (words)
+    unsigned long long *scan_desc; uint32_t scan_words;
+    Counters *cnt;
+};
+__device__ __forceinline__ void end_of_tick(const TickDuty &D, const uint32_t *n_ptr) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    uint4 *c4 = reinterpret_cast<uint4 *>(D.cells);
+    const uint32_t n4 = D.ncells / 4;
+    for (uint32_t i = tid; i < n4; i += nth) c4[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = n4 * 4 + tid; i < D.ncells; i += nth) D.cells[i] = 0;
+    for (uint32_t i = tid; i < D.nbits; i += nth) { D.bits_a[i] = 0; D.bits_b[i] = 0; }
+    for (uint32_t i = tid; i < D.scan_words; i += nth) D.scan_desc[i] = 0ull;
+    if (tid == 0) { D.cnt->n = *n_ptr; D.cnt->n_wall = 0; }
+}
+
 // ---- counter-based pair noise (the production definition; oracle/step_oracle.c restates it) -------------
 // Host side: tick_key = splitmix64 finalizer of (seed, tick).  Device side, per DIRECTED pair (i <- j), 32-bit
 // arithmetic only: the two uids are spread with distinct odd multipliers, keyed with the two halves of tick_key

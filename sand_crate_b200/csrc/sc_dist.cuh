@@ -41,53 +41,33 @@ __device__ __forceinline__ void wire_push(WireHeader *h, WireRec *recs, uint32_t
     recs[k] = r;
 }
 
-// One read-mostly pass over the particle arrays, in place (no compaction: the arrays keep the previous tick's sorted
-// order, which is what makes the next tick's gathers nearly coalesced):
+// A pass over the particle arrays, in place (no compaction: the arrays keep the previous tick's sorted order, which is
+// what makes the next tick's gathers nearly coalesced):
 //   last tick's ghost      -> killed: its x becomes +inf, so this tick's remove_particles pass (k_prepass) drops it
 //   row left the strip     -> MIGRANT record for the neighbor; stays here, re-tagged as a ghost, for this tick
 //   owned, near a cut      -> HALO record(s)
 // n_in_ptr = live count left by the previous tick (its scan total) or cnt->n; it is copied to cnt->n, where the
 // unpack kernel appends what the neighbors send.  The send headers' counts are zero on entry (k_dist_unpack re-arms
 // them once the previous tick's buffers have left).
-template <typename Real>
-__global__ void __launch_bounds__(SC_BLOCK)
-k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D,
-            double2 *pos, const typename Vec2<Real>::type *vel,
-            uint32_t *uid, WireHeader *lo_hdr, WireHeader *hi_hdr) {
-    pdl_enter();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_in = *n_in_ptr;
-    if (i == 0) cnt->n = n_in;
-    if (i >= n_in) return;
-    const uint32_t u = uid[i];
-    if (u & SC_GHOST_BIT) {  // its owner has the authoritative copy
-        pos[i].x = __longlong_as_double(0x7FF0000000000000LL);
-        return;
-    }
-    const double2 p = pos[i];
-    const double fr = floor_div(p.y, g);
-    const long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : 0;  // NaN: stays where it is
-    WireRec *lo_recs = reinterpret_cast<WireRec *>(lo_hdr + 1), *hi_recs = reinterpret_cast<WireRec *>(hi_hdr + 1);
-    const bool below = row < D.row_lo && D.has_lo, above = row >= D.row_hi && D.has_hi;
-    if (below || above) {
-        const typename Vec2<Real>::type v = vel[i];
-        if (below) {
-            if (row < D.row_lo - D.halo) lo_hdr->too_far = 1u;
-            wire_push(lo_hdr, lo_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
-        } else {
-            if (row >= D.row_hi + D.halo) hi_hdr->too_far = 1u;
-            wire_push(hi_hdr, hi_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
-        }
-        uid[i] = u | SC_GHOST_BIT;
-    } else {
-        const bool to_lo = D.has_lo && row < D.row_lo + D.halo, to_hi = D.has_hi && row >= D.row_hi - D.halo;
-        if (to_lo || to_hi) {
-            const typename Vec2<Real>::type v = vel[i];
-            if (to_lo) wire_push(lo_hdr, lo_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
-            if (to_hi) wire_push(hi_hdr, hi_recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
-        }
-    }
-}
+//
+// Only the rows near a cut can hold any of the three.  The arrays are in the last tick's sorted order (cell rows
+// ascending), so those rows are two index ranges, [0, A) and [B, n), read off the last tick's cell boundaries
+// (PackRange): the kernel then touches a few percent of the particles instead of all of them.  Without a valid search
+// state (first tick, after a re-grid) the pass covers everything.
+//
+// kDirect (the NVLink transport): the records are written straight into the neighbor's receive buffer through a
+// peer-mapped pointer - pack and transfer are ONE kernel, the bytes cross NVLink as they are produced - and the last
+// block to finish publishes the record count and raises the neighbor's flag (release, system scope); the neighbor's
+// unpack kernel, running on its own GPU, acquires it.
+struct PackRange {
+    const uint32_t *cell_start;  // last tick's cell boundaries, or NULL: cover all particles
+    uint32_t cell_a, cell_b;     // first cell of the first row above the lower boundary zone / of the upper boundary zone
+};
+struct PackOut {
+    WireHeader *hdr;   // LOCAL header: record counter (atomic), sticky overflow / too_far marks
+    WireRec *recs;     // where the records go: the local send buffer, or the neighbor's receive buffer (kDirect)
+    WireHeader *peer_hdr; uint32_t *peer_flag;  // kDirect only
+};
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -96,6 +76,75 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+template <typename Real, bool kDirect>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRange R,
+            double2 *pos, const typename Vec2<Real>::type *vel,
+            uint32_t *uid, PackOut lo, PackOut hi, uint32_t *done, uint32_t value) {
+    pdl_enter();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_in = *n_in_ptr;
+    if (idx == 0) cnt->n = n_in;
+    uint32_t i = idx;
+    if (R.cell_start) {
+        uint32_t A = D.has_lo ? R.cell_start[R.cell_a] : 0u, B = D.has_hi ? R.cell_start[R.cell_b] : n_in;
+        if (B > n_in) B = n_in;
+        if (A > B) A = B;
+        if (idx == 0 && A + (n_in - B) > gridDim.x * blockDim.x) { lo.hdr->overflow = 1u; hi.hdr->overflow = 1u; }
+        i = idx < A ? idx : B + (idx - A);
+    }
+    if (i < n_in) {
+        const uint32_t u = uid[i];
+        if (u & SC_GHOST_BIT) {  // its owner has the authoritative copy
+            pos[i].x = __longlong_as_double(0x7FF0000000000000LL);
+        } else {
+            const double2 p = pos[i];
+            const double fr = floor_div(p.y, g);
+            const long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : 0;  // NaN: stays where it is
+            const bool below = row < D.row_lo && D.has_lo, above = row >= D.row_hi && D.has_hi;
+            if (below || above) {
+                const typename Vec2<Real>::type v = vel[i];
+                if (below) {
+                    if (row < D.row_lo - D.halo) lo.hdr->too_far = 1u;
+                    wire_push(lo.hdr, lo.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
+                } else {
+                    if (row >= D.row_hi + D.halo) hi.hdr->too_far = 1u;
+                    wire_push(hi.hdr, hi.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
+                }
+                uid[i] = u | SC_GHOST_BIT;
+            } else {
+                const bool to_lo = D.has_lo && row < D.row_lo + D.halo, to_hi = D.has_hi && row >= D.row_hi - D.halo;
+                if (to_lo || to_hi) {
+                    const typename Vec2<Real>::type v = vel[i];
+                    if (to_lo) wire_push(lo.hdr, lo.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
+                    if (to_hi) wire_push(hi.hdr, hi.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_HALO);
+                }
+            }
+        }
+    }
+    if constexpr (kDirect) {
+        __threadfence_system();  // this block's records have reached the neighbor before it is counted as done
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t prev = atomicAdd(done, 1u);
+            if (prev == gridDim.x - 1) {  // every block's records are out: publish the counts, raise the flags
+                *done = 0u;
+                __threadfence();
+                if (D.has_lo) {
+                    const uint32_t c = *(volatile uint32_t *)&lo.hdr->count;
+                    lo.peer_hdr->count = c < D.cap ? c : D.cap;
+                    st_release_sys(lo.peer_flag, value);
+                }
+                if (D.has_hi) {
+                    const uint32_t c = *(volatile uint32_t *)&hi.hdr->count;
+                    hi.peer_hdr->count = c < D.cap ? c : D.cap;
+                    st_release_sys(hi.peer_flag, value);
+                }
+            }
+        }
+    }
 }
 
 struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == NULL: the data is already there

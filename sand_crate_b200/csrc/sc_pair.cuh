@@ -335,9 +335,8 @@ k_density(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
 // bounce, continuous collision, integration.  `visc(vx, vy, ax, ay)` supplies sum_j (v_j - v) (crate.py:319-323).
 template <typename Real, bool kMonitor, typename ViscFn>
 __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx, Real ty, Real qx, Real qy,
-                                           const DevParams &P, const WallParams &W, const double2 *pos,
-                                           const typename Vec2<Real>::type *vel,
-                                           const uint32_t *wall_bits,
+                                           const DevParams &P, const WallParams &W, const double2 ps,
+                                           const typename Vec2<Real>::type v0, const bool touching,
                                            const uint32_t *wall_slot,
                                            const double2 *wall_pre, double2 *pos_out,
                                            typename Vec2<Real>::type *vel_out,
@@ -357,7 +356,6 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
     // (crate.py:216 runs before 202-211 and the vectors are never refreshed)
     int V = 0;
     double wnx = 0, wny = 0, wux = 0, wuy = 0;  // sequential sums for np.mean (crate.py:249-250)
-    const bool touching = (wall_bits[s >> 5] >> (s & 31)) & 1u;
     if (touching) {
         const double2 pre = wall_pre[wall_slot[s]];
         int nb[SC_MAX_BODIES];
@@ -390,10 +388,6 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
         }
     }
 
-    // own position / velocity are only needed from here on: loading them late keeps the pair loop's register
-    // footprint (and with it the occupancy that hides the gather latency) small
-    const double2 ps = pos[s];
-    const R2 v0 = vel[s];
     const Real dt = (Real)P.dt;
     Real vx = v0.x, vy = v0.y;
     if constexpr (kMonitor) { mpx = (double)vx; mpy = (double)vy; }
@@ -487,8 +481,9 @@ k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W
         const PS<Real> *ps_in, const uint32_t *wall_bits,
         const uint32_t *wall_slot, const double2 *wall_pre,
         double2 *pos_out, typename Vec2<Real>::type *vel_out,
-        double *monitor) {
+        double *monitor, TickDuty duty) {
     pdl_enter();
+    end_of_tick(duty, n_ptr);
     typedef typename Vec2<Real>::type R2;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= *n_ptr) return;
@@ -536,7 +531,12 @@ k_force(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W
             }
     }
 
-    force_tail<Real, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
+    // own position / velocity are only needed from here on: loading them late keeps the pair loop's register
+    // footprint (and with it the occupancy that hides the gather latency of this untiled kernel) small
+    const double2 ps_own = pos[s];
+    const R2 v_own = vel[s];
+    const bool touching = (wall_bits[s >> 5] >> (s & 31)) & 1u;
+    force_tail<Real, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, ps_own, v_own, touching, wall_slot, wall_pre, pos_out, vel_out,
                                monitor, n_ptr, [&](Real vx, Real vy, Real &ax, Real &ay) {
         if constexpr (sizeof(Real) == 8) {
             for (int q = 0; q < K; ++q) {

@@ -24,9 +24,15 @@ __global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it i
 k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
           double2 *pos, uint32_t *cell_key, uint32_t *slot,
           uint32_t *cell_count, uint32_t *wall_bits, uint32_t *wall_slot,
-          double2 *wall_pre) {
+          double2 *wall_pre, uint32_t cap) {
     pdl_enter();
-    const uint32_t n = cnt->n;
+    // the strip exchange appends with an atomic counter and only flags an overflow: every kernel bounds its indices by
+    // the count, so the count itself must never exceed the arrays
+    const uint32_t n = cnt->n < cap ? cnt->n : cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (cnt->n > cap) cnt->overflow = 1u;
+        cnt->pair_cursor = 0; cnt->n_untiled = 0;  // consumed by this tick's density kernel
+    }
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
     double2 p[SC_PREPASS_ILP];
     uint32_t c[SC_PREPASS_ILP];
@@ -44,7 +50,6 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
             const bool out = (p[u].x < P.box_lo) | (p[u].x > P.box_hi) | (p[u].y < P.box_lo) | (p[u].y > P.box_hi);
             if (out) {
                 cell_key[i] = SC_INVALID_CELL;
-                atomicAdd(&cnt->n_removed, 1u);
                 continue;
             }
             // one test for the bulk of the liquid: inside a rectangle that no segment's touch zone reaches
@@ -187,9 +192,9 @@ k_scan_lookback(uint32_t *a, uint32_t n, unsigned long long *desc,
 #define SC_PLACE_ILP 4
 __global__ void __launch_bounds__(SC_BLOCK)
 k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
-        const uint32_t *cell_start, uint32_t *tmpidx) {
+        const uint32_t *cell_start, uint32_t *tmpidx, uint32_t cap) {
     pdl_enter();
-    const uint32_t n = cnt->n;
+    const uint32_t n = cnt->n < cap ? cnt->n : cap;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
     uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP];
 #pragma unroll
@@ -291,6 +296,16 @@ k_count_neighbors(Counters *cnt, Grid g, const uint32_t *cell_start,
         for (int k = 0; k < K; ++k) list_sorted[(size_t)s * SC_MAX_NEIGHBORS + k] = lst.get(k) & SC_IDX_MASK;
     count_by_rank[rank_of_uid[uid[s]]] = (uint32_t)K;
     atomicAdd(&cnt->n_pairs, (uint32_t)K);
+}
+
+// sum of the per-particle pair counts of the last tick (on demand: the step itself keeps no running total)
+__global__ void __launch_bounds__(SC_BLOCK)
+k_sum_pair_counts(const uint32_t *n_ptr, const uint8_t *pair_cnt, uint32_t *total) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = s < *n_ptr ? pair_cnt[s] : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
 }
 
 // ---- scatter from sorted order to original (rank) order for host-visible arrays -------------------------------
@@ -407,9 +422,9 @@ __global__ void __launch_bounds__(SC_BLOCK) k_iota(uint32_t *a, uint32_t base, u
     if (i < n) a[i] = base + i;
 }
 
-// Start of a tick, one launch: carry the live count over from the previous tick's scan total (when the host has
-// not touched the particle set in between), reset the per-tick counters, zero the cell histogram and both wall
-// bitmaps.  Entry [ncells] (the previous total) is deliberately not zeroed: the scan rewrites it.
+// COLD start of a tick (the first tick of a context, or the first after the cell grid was rebuilt): what the previous
+// tick's force kernel would have done (end_of_tick in sc_common.cuh), as a launch of its own.  `carry_count` is kept
+// for the standalone search.
 __global__ void __launch_bounds__(SC_BLOCK)
 k_begin_tick(Counters *cnt, uint32_t *cell_count, uint32_t ncells, int carry_count,
              uint32_t *bits_a, uint32_t *bits_b, uint32_t nbits_words,
@@ -418,8 +433,6 @@ k_begin_tick(Counters *cnt, uint32_t *cell_count, uint32_t ncells, int carry_cou
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
-        // the strip exchange appends with an atomic counter and only flags an overflow: every later kernel bounds its
-        // indices by cnt->n, so the count itself must never exceed the arrays
         if (cnt->n > cap) { cnt->n = cap; cnt->overflow = 1u; }
         cnt->n_removed = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0; cnt->n_untiled = 0;
     }

@@ -32,6 +32,9 @@
 namespace sc {
 
 #define SC_TILE_CAP (5 * SC_TILE)              // staged particles per block (3 windows of ~SC_TILE + a few cells each)
+#ifndef SC_K5_ROWS
+#define SC_K5_ROWS 6                           // pair-record slots of a block that K5 stages in shared memory
+#endif
 #define SC_TILE_CELLS (SC_TILE + SC_TILE / 2 + 64)  // staged cell boundaries per row (blocks that wrap around a row end
                                                // read them from global)
 
@@ -121,6 +124,11 @@ template <> __device__ __forceinline__ float4 SmemAcc<float4>::get(uint32_t L) c
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + L * 16u));
     return v;
 }
+template <> __device__ __forceinline__ uint2 SmemAcc<uint2>::get(uint32_t L) const {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr + L * 8u));
+    return v;
+}
 template <> __device__ __forceinline__ float2 SmemAcc<float2>::get(uint32_t L) const {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr + L * 8u));
@@ -152,8 +160,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 template <int kNoise, class Acc, class List>
 __device__ __forceinline__ void density_particle(const Acc &A, List lst, const TileWindows &w, bool live, uint32_t s,
                                                  const uint32_t (&b)[6], const Grid &g, const DevParams &P,
-                                                 Counters *cnt, const double2 *pos,
-                                                 uint2 *pair_rec, uint32_t *pair_off,
+                                                 const double2 *pos, uint2 *pair_rec,
                                                  uint8_t *pair_cnt, PS<float> *ps_out) {
     const float df = (float)g.d;
     const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
@@ -190,28 +197,16 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
 #undef SC_TILE_RANGE
         K = count;
     }
-    // the warp's records go to one contiguous chunk of the pair buffer (one atomic per warp); where the chunk lands
-    // is arbitrary, but it is only ever reached through pair_off
-    const int lane = threadIdx.x & 31;
-    uint32_t inc = (uint32_t)K;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&cnt->pair_cursor, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
+    // Records are SLOT-MAJOR inside the block's own region of the pair buffer: record k of thread t sits at
+    // (block * 20 + k) * SC_TILE + t.  No allocation (no scan, no atomic, no offset array), a warp's stores of one slot
+    // are one contiguous 256-byte run, and K5 can bulk-copy the first slots of the whole block without knowing anything.
     if (!live) return;
-    const uint32_t off = base + inc - (uint32_t)K;
-    pair_off[s] = off;
     pair_cnt[s] = (uint8_t)K;
     const uint32_t uid_s = __float_as_uint(me.w);
     const float inv_d = (float)(1.0 / P.d);
     const float amp = (float)(P.d * P.level);
     float ax = 0, ay = 0, psum = 0;
-    uint2 *out = pair_rec + off;
+    uint2 *out = pair_rec + (size_t)blockIdx.x * (SC_MAX_NEIGHBORS * SC_TILE) + threadIdx.x;
     for (int k = 0; k < K; ++k) {
         uint32_t L, code;  // code = dr + 1
         lst.get(k, L, code);
@@ -230,7 +225,7 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         const float nx = rx * inv, ny = ry * inv;
         const float cl = __saturatef((q * inv) * inv_d);  // np.clip(dist / d, 0, 1), crate.py:270
         const float wgt = 1.0f - cl;
-        out[k] = pair_encode(L, nx, ny);
+        out[k * SC_TILE] = pair_encode(L, nx, ny);
         psum += wgt;
         const float c = cl * wgt;  // (1 - w) w, crate.py:340
         ax = fmaf(c, nx, ax);
@@ -257,8 +252,7 @@ __global__ void __launch_bounds__(SC_TILE, SC_TILE_RESIDENT / SC_TILE)
 k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
                const BlockDesc *desc, const double2 *pos,
                const SearchRec *rec, const uint32_t *cell_key,
-               uint2 *pair_rec, uint32_t *pair_off, uint8_t *pair_cnt,
-               PS<float> *ps_out) {
+               uint2 *pair_rec, uint8_t *pair_cnt, PS<float> *ps_out) {
     pdl_enter();
     // staged: [records 20 KB | cell boundaries 4.7 KB | 16-bit lists 10 KB]; pass-through: [32-bit lists 20 KB]
     __shared__ __align__(128) unsigned char s_raw[SC_TILE_SMEM_K4];
@@ -315,7 +309,7 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
             b[4] = r2[0] + d2; b[5] = r2[3] + d2;
         }
         density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr(s_rec)}, TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live,
-                                 s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
+                                 s, b, g, P, pos, pair_rec, pair_cnt, ps_out);
     } else {
         if (threadIdx.x == 0) atomicAdd(&cnt->n_untiled, 1u);  // rare; lets a test prove this path ran
         if (live) {
@@ -326,7 +320,7 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
         }
         density_particle<kNoise>(GmemAcc<SearchRec>{rec},
                                  TileList<uint32_t, 28>{reinterpret_cast<uint32_t *>(s_raw) + threadIdx.x}, w,
-                                 live, s, b, g, P, cnt, pos, pair_rec, pair_off, pair_cnt, ps_out);
+                                 live, s, b, g, P, pos, pair_rec, pair_cnt, ps_out);
     }
 }
 
@@ -341,12 +335,14 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
 template <bool kMonitor>
 __global__ void __launch_bounds__(SC_TILE, 4)
 k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W, const BlockDesc *desc,
-             const double2 *pos, const float2 *vel, const uint2 *pair_rec, const uint32_t *pair_off,
+             const double2 *pos, const float2 *vel, const uint2 *pair_rec,
              const uint8_t *pair_cnt, const PS<float> *ps_in, const uint32_t *wall_bits, const uint32_t *wall_slot,
-             const double2 *wall_pre, double2 *pos_out, float2 *vel_out, double *monitor) {
+             const double2 *wall_pre, double2 *pos_out, float2 *vel_out, double *monitor, TickDuty duty) {
     pdl_enter();
+    end_of_tick(duty, n_ptr);
     __shared__ __align__(128) float4 s_ps[SC_TILE_CAP];
     __shared__ __align__(128) float2 s_vel[SC_TILE_CAP];
+    __shared__ __align__(128) uint2 s_pair[SC_K5_ROWS * SC_TILE];  // the block's first SC_K5_ROWS record slots
     __shared__ __align__(8) unsigned long long s_bar;
     const uint32_t b0 = blockIdx.x * SC_TILE;
     const uint32_t n = *n_ptr;
@@ -355,27 +351,33 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
     const bool live = s < n;
     const TileWindows w = tile_windows(desc + blockIdx.x);
     const uint32_t bar = smem_addr(&s_bar);
-    if (w.staged) {
-        if (threadIdx.x == 0) mbar_init(bar, 1u);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, w.total * 24u);
+    const uint2 *my_rec = pair_rec + (size_t)blockIdx.x * (SC_MAX_NEIGHBORS * SC_TILE) + threadIdx.x;
+    if (threadIdx.x == 0) mbar_init(bar, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (w.staged ? w.total * 24u : 0u) + SC_K5_ROWS * SC_TILE * 8u);
+        bulk_g2s(smem_addr(s_pair), my_rec, SC_K5_ROWS * SC_TILE * 8u, bar);
+        if (w.staged) {
             stage_windows(w, ps_in, 16u, smem_addr(s_ps), bar);
             stage_windows(w, vel, 8u, smem_addr(s_vel), bar);
         }
     }
-    // own record, straight from global memory while the copies fly
+    // everything this thread needs of its OWN particle, straight from global memory while the copies fly (the block is
+    // a chain of latencies - descriptor, copies, these loads - and occupancy is set by shared memory, not registers:
+    // nothing is gained by loading late)
     PS<float> me;
-    uint32_t off = 0;
     int K = 0;
-    uint2 rnext = make_uint2(0u, 0u);
+    double2 ps_own = make_double2(0, 0);
+    float2 v_own = make_float2(0, 0);
+    bool touching = false;
     if (live) {
         me = ps_in[s];
-        off = pair_off[s];
         K = pair_cnt[s];
-        if (K) rnext = pair_rec[off];
+        ps_own = pos[s];
+        v_own = vel[s];
+        touching = (wall_bits[s >> 5] >> (s & 31)) & 1u;
     }
-    if (w.staged) mbar_wait(bar, 0u);
+    mbar_wait(bar, 0u);
     if (!live) return;
     const float p_i = me.p;
     const float smooth = (float)P.smooth, two_target = (float)(2 * P.target);
@@ -384,30 +386,40 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
     float sum_vx = 0, sum_vy = 0;  // sum of neighbor velocities (F6)
     const SmemAcc<float4> Aps{smem_addr(s_ps)};
     const SmemAcc<float2> Avel{smem_addr(s_vel)};
-    for (int k = 0; k < K; ++k) {
-        const uint2 r = rnext;
-        if (k + 1 < K) rnext = pair_rec[off + k + 1];  // the next record is in flight while this pair is evaluated
+    const SmemAcc<uint2> Arec{smem_addr(s_pair) + threadIdx.x * 8u};
+    // one pair: F3 pass 2 (crate.py:347-353), F5 (301-306), F6's neighbor velocity sum (319-323), in list order
+    auto pair = [&](int k, uint2 r, auto get_ps, auto get_vel) {
         uint32_t L;
         float nx, ny;
         pair_decode(r, L, nx, ny);
-        float4 nb;
-        float2 vj;
-        if (w.staged) { nb = Aps.get(L); vj = Avel.get(L); }
-        else { const PS<float> g_ = ps_in[L]; nb = make_float4(g_.p, g_.sx, g_.sy, 0.0f); vj = vel[L]; }
-        // F3 pass 2, crate.py:347-353
+        const float4 nb = get_ps(L);
+        const float2 vj = get_vel(L);
         const float ddx = me.sx - nb.y, ddy = me.sy - nb.z;
         const float align = (ddx * nx + ddy * ny) * smooth;
         const float fix = nb.x + p_i - two_target;
         const float cc = align + fix;
         const float ex = cc * nx, ey = cc * ny;
-        // F5, crate.py:301-306
         const float ps_ = p_i + nb.x;
         const float fx = nx * ps_, fy = ny * ps_;
         if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
         else { tx += ex; ty += ey; qx += fx; qy += fy; }
         sum_vx += vj.x; sum_vy += vj.y;
+    };
+    // the loop is unswitched on the two block-uniform / rare conditions: staged or pass-through block, and record slots
+    // beyond the staged rows (K > SC_K5_ROWS: one particle in six at rest density), which come from global memory
+    const int Ks = K < SC_K5_ROWS ? K : SC_K5_ROWS;
+    if (w.staged) {
+        auto gp = [&](uint32_t L) { return Aps.get(L); };
+        auto gv = [&](uint32_t L) { return Avel.get(L); };
+        for (int k = 0; k < Ks; ++k) pair(k, Arec.get((uint32_t)k * SC_TILE), gp, gv);
+        for (int k = SC_K5_ROWS; k < K; ++k) pair(k, my_rec[k * SC_TILE], gp, gv);
+    } else {
+        auto gp = [&](uint32_t L) { const PS<float> g_ = ps_in[L]; return make_float4(g_.p, g_.sx, g_.sy, 0.0f); };
+        auto gv = [&](uint32_t L) { return vel[L]; };
+        for (int k = 0; k < Ks; ++k) pair(k, Arec.get((uint32_t)k * SC_TILE), gp, gv);
+        for (int k = SC_K5_ROWS; k < K; ++k) pair(k, my_rec[k * SC_TILE], gp, gv);
     }
-    force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, pos, vel, wall_bits, wall_slot, wall_pre, pos_out, vel_out,
+    force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, ps_own, v_own, touching, wall_slot, wall_pre, pos_out, vel_out,
                                 monitor, n_ptr, [&](float vx, float vy, float &ax, float &ay) {
         ax = sum_vx - (float)K * vx;
         ay = sum_vy - (float)K * vy;

@@ -256,7 +256,7 @@ class StripDomain:
         if self.has_hi:
             peer = self._peer[self.rank + 1]
             hi = (self.send_hi, peer + data, peer + 64 * (2 * par))
-        self.ctx.dist_push(lo, hi, value)
+        self.ctx.dist_pack_push(lo, hi, value)   # pack and NVLink transfer are one kernel
         mine = self._peer[self.rank]
         self.ctx.dist_unpack_flagged((mine + data, mine + 64 * (2 * par)) if self.has_lo else None,
                                      (mine + data + self._slot, mine + 64 * (2 * par + 1)) if self.has_hi else None,
@@ -315,10 +315,10 @@ class StripDomain:
                 self.rebalance()
             if self.cuts != self.target_cuts:
                 self._slide_cuts()
-            self.ctx.dist_pack(self.send_lo, self.send_hi)
             if self._symm is not None:
                 self._exchange_p2p()
             else:
+                self.ctx.dist_pack(self.send_lo, self.send_hi)
                 self.exchange()
                 self.ctx.dist_unpack(self.recv_lo, self.recv_hi)
         self.ctx.step()
