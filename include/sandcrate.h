@@ -83,6 +83,27 @@ int sc_particle_count(sc_ctx *ctx, int64_t *n);                     /* crate.py:
 int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *pressure, int64_t cap, int64_t *n);
 int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n);
 
+/* create_new_particles + ParticleSource.generate_particles (crate.py:138-147, particle_source.py:17-24) on the DEVICE,
+ * for the counter-based production mode (the reference-stream mode keeps drawing on the host and appends with
+ * sc_append_particles).  `count` = the emission count the caller drew for this tick from the counter stream
+ * (sc_source_stream element 0 through the binomial inverse CDF: sand_crate_b200/particle_source.py); the device clamps
+ * it to max_particles - particle_count exactly where the reference does (count before this tick's removal, after the
+ * earlier sources), draws positions / velocities from stream elements 1 + 4k + {0, 1, 2, 3} and appends.  No host
+ * synchronisation: a tick with sources costs one extra one-block launch.  Uses the seed of sc_set_noise and the tick
+ * of sc_set_tick. */
+typedef struct sc_source {
+    double position_x, position_y; /* ParticleSource.position */
+    double radius;                 /* .radius */
+    double velocity_x, velocity_y; /* .velocity */
+    double velocity_noise;         /* .noise */
+    int32_t count;                 /* drawn emission count of this tick */
+    uint32_t index;                /* position of the source in world.particle_sources (keys its stream) */
+} sc_source;
+#define SC_MAX_SOURCES 8
+int sc_emit_particles(sc_ctx *ctx, const sc_source *sources, int nsources, int64_t max_particles);
+/* element j of source `source_index`'s counter stream at (seed, tick) as a uniform in [0, 1); returns the stream key */
+uint64_t sc_source_stream(uint64_t seed, uint64_t tick, uint32_t source_index, uint64_t j, double *u);
+
 /* Page-locked host memory for the buffers handed to sc_set_state / sc_append_particles / sc_get_state /
  * sc_dist_get_owned.  No reference counterpart (the reference never leaves the host); with pageable buffers the
  * copies are staged by the driver and run at a fraction of the PCIe rate.  The host mirror keeps its readback arrays
@@ -143,6 +164,7 @@ int sc_profile_enable(sc_ctx *ctx, int on);
 int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int slots);
 const char *sc_profile_name(int slot);
 int64_t sc_launch_count(const sc_ctx *ctx); /* kernels launched by this context so far */
+int64_t sc_sync_count(const sc_ctx *ctx);   /* times an entry point made the host wait for the stream so far */
 /* sum(K_i) of the last tick = rows of the reference's `colliders` lists (crate.py:161-175) over the particles this
  * context holds (ghost copies of a strip included).  Synchronises. */
 int sc_last_pair_count(sc_ctx *ctx, int64_t *n_pairs);

@@ -62,6 +62,12 @@ def lib():
         L.oc_pair_noise.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, dp, dp]
         L.oc_pair_noise.restype = None
         L.oc_num_threads.restype = C.c_int
+        L.oc_source_key.argtypes = [C.c_uint64, C.c_uint32]
+        L.oc_source_key.restype = C.c_uint64
+        L.oc_source_uniform.argtypes = [C.c_uint64, C.c_uint64]
+        L.oc_source_uniform.restype = C.c_double
+        L.oc_emit_counter.argtypes = [C.c_uint64, C.c_int, dp, ip, C.POINTER(C.c_uint32), C.c_int64, C.c_int64, dp, dp]
+        L.oc_emit_counter.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -125,6 +131,58 @@ def remove_particles(pos, vel, radius):
 
 def tick_key(seed: int, tick: int) -> int:
     return int(lib().oc_tick_key(C.c_uint64(seed), C.c_uint64(tick)))
+
+
+def source_uniform(seed: int, tick: int, source_index: int, j: int) -> float:
+    L = lib()
+    return float(L.oc_source_uniform(L.oc_source_key(C.c_uint64(tick_key(seed, tick)), C.c_uint32(source_index)),
+                                     C.c_uint64(j)))
+
+
+def source_count(u: float, flow: float, dt: float) -> int:
+    """Binomial(flow, dt) through its inverse CDF at u (the emission count of particle_source.py:18 before the clamp):
+    the smallest k whose cumulative probability reaches u."""
+    trials, p = int(flow), float(dt)
+    if trials <= 0 or p <= 0:
+        return 0
+    if p >= 1:
+        return trials
+    import math
+    q = 1.0 - p
+    mass = math.pow(q, trials)
+    cdf, k = mass, 0
+    while u > cdf and k < trials:
+        k += 1
+        mass *= (trials - k + 1) / k * (p / q)
+        cdf += mass
+    return k
+
+
+def emit_counter(seed: int, tick: int, sources, dt: float, particle_count: int, max_particles: int):
+    """The counter-stream version of create_new_particles for one tick.  sources: the world's particle_sources dicts
+    (radius, position, velocity, flow, active_ticks, noise).  Returns (pos, vel) of the appended rows."""
+    rows, counts, index = [], [], []
+    for q, s in enumerate(sources):
+        if s["active_ticks"] <= tick:           # crate.py:140
+            continue
+        n = source_count(source_uniform(seed, tick, q, 0), s["flow"], dt)
+        if n == 0:
+            continue
+        rows.append([s["position"][0], s["position"][1], s["radius"], s["velocity"][0], s["velocity"][1],
+                     s.get("noise", 0.05)])
+        counts.append(n)
+        index.append(q)
+    if not rows:
+        return np.zeros((0, 2)), np.zeros((0, 2))
+    src = np.ascontiguousarray(rows, dtype=np.float64)
+    cnt = np.ascontiguousarray(counts, dtype=np.int32)
+    idx = np.ascontiguousarray(index, dtype=np.uint32)
+    pos = np.zeros((int(cnt.sum()), 2))
+    vel = np.zeros((int(cnt.sum()), 2))
+    m = lib().oc_emit_counter(C.c_uint64(tick_key(seed, tick)), len(rows), _dp(src), _ip(cnt),
+                              idx.ctypes.data_as(C.POINTER(C.c_uint32)), int(particle_count), int(max_particles),
+                              _dp(pos), _dp(vel))
+    return pos[:m].copy(), vel[:m].copy()
 
 
 def pair_noise(tkey: int, uid_i: int, uid_j: int):

@@ -49,6 +49,43 @@ static inline uint32_t oc_lowbias32(uint32_t x) {
     x ^= x >> 16;
     return x;
 }
+/* counter-based particle sources: the PRODUCT's production definition (sc_emit_particles, csrc/sc_sort.cuh k_emit,  */
+/* csrc/sc_common.cuh source_key / source_uniform), restated.  What it models is the reference's                     */
+/* create_new_particles + ParticleSource.generate_particles (crate.py:138-147, particle_source.py:17-24) with the     */
+/* global MT19937 stream replaced by a counter stream: element 0 of a source's stream is the uniform behind its       */
+/* Binomial(flow, dt) emission count (inverse CDF, evaluated by the caller), elements 1 + 4k + {0,1,2,3} are the      */
+/* position / velocity jitters of its k-th particle of the tick.                                                      */
+uint64_t oc_source_key(uint64_t tick_key, uint32_t q) {
+    return oc_mix64(tick_key ^ (0xD1B54A32D192ED03ULL * (uint64_t)(q + 1u)));
+}
+double oc_source_uniform(uint64_t skey, uint64_t j) {
+    return (double)(oc_mix64(skey + (j + 1ull) * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
+}
+/* src: nsrc x 6 (position x, y, radius, velocity x, y, noise); count / index per source; P = particle count before the */
+/* tick's removal.  Appends rows in source order; returns how many.  pos_out / vel_out: room for sum(count) rows.      */
+int64_t oc_emit_counter(uint64_t tick_key, int nsrc, const double *src, const int32_t *count, const uint32_t *index,
+                        int64_t P, int64_t max_particles, double *pos_out, double *vel_out) {
+    int64_t out = 0;
+    for (int q = 0; q < nsrc; ++q) {
+        const double *S = src + 6 * q;
+        int64_t room = max_particles - P;               /* crate.py:143: max_particles - particle_count */
+        if (room < 0) room = 0;
+        const int64_t a = count[q] < room ? count[q] : room;   /* particle_source.py:18 */
+        const uint64_t key = oc_source_key(tick_key, index[q]);
+        for (int64_t k = 0; k < a; ++k) {
+            const double ux = oc_source_uniform(key, 1 + 4 * (uint64_t)k), uy = oc_source_uniform(key, 2 + 4 * (uint64_t)k);
+            const double wx = oc_source_uniform(key, 3 + 4 * (uint64_t)k), wy = oc_source_uniform(key, 4 + 4 * (uint64_t)k);
+            pos_out[2 * out] = (ux - 0.5) * S[2] + S[0];        /* particle_source.py:21 */
+            pos_out[2 * out + 1] = (uy - 0.5) * S[2] + S[1];
+            vel_out[2 * out] = S[3] + (wx - 0.5) * S[5];        /* particle_source.py:22-23 */
+            vel_out[2 * out + 1] = S[4] + (wy - 0.5) * S[5];
+            ++out;
+        }
+        P += a;
+    }
+    return out;
+}
+
 void oc_pair_noise(uint64_t tick_key, uint32_t uid_i, uint32_t uid_j, double *ux, double *uy) {
     const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
     const uint32_t h = oc_lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^

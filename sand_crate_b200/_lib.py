@@ -31,6 +31,12 @@ class ScParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in PARAM_FIELDS]
 
 
+class ScSource(C.Structure):
+    _fields_ = [("position_x", C.c_double), ("position_y", C.c_double), ("radius", C.c_double),
+                ("velocity_x", C.c_double), ("velocity_y", C.c_double), ("velocity_noise", C.c_double),
+                ("count", C.c_int32), ("index", C.c_uint32)]
+
+
 class SandCrateError(RuntimeError):
     pass
 
@@ -56,6 +62,8 @@ SIGNATURES = {
     "sc_set_state": (C.c_int, [_ctx, _dp, _dp, C.c_int64]),
     "sc_append_particles": (C.c_int, [_ctx, _dp, _dp, C.c_int64]),
     "sc_particle_count": (C.c_int, [_ctx, _lp]),
+    "sc_emit_particles": (C.c_int, [_ctx, C.POINTER(ScSource), C.c_int, C.c_int64]),
+    "sc_source_stream": (C.c_uint64, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, _dp]),
     "sc_get_state": (C.c_int, [_ctx, _dp, _dp, _dp, C.c_int64, _lp]),
     "sc_get_uids": (C.c_int, [_ctx, _up, C.c_int64, _lp]),
     "sc_step": (C.c_int, [_ctx]),
@@ -88,6 +96,7 @@ SIGNATURES = {
     "sc_profile_read": (C.c_int, [_ctx, _lp, _dp, C.c_int]),
     "sc_profile_name": (C.c_char_p, [C.c_int]),
     "sc_launch_count": (C.c_int64, [_ctx]),
+    "sc_sync_count": (C.c_int64, [_ctx]),
     "sc_last_pair_count": (C.c_int, [_ctx, _lp]),
     "sc_debug_rerun": (C.c_double, [_ctx, C.c_int, C.c_int]),
     "sc_debug_untiled_blocks": (C.c_int64, [_ctx]),
@@ -225,6 +234,11 @@ class Context:
         pos, vel = _f64(pos, 2), _f64(vel, 2)
         assert pos.shape == vel.shape
         self._ck(self._L.sc_append_particles(self._h, _ptr(pos, _dp), _ptr(vel, _dp), pos.shape[0]))
+
+    def emit_particles(self, records, max_particles: int):
+        """records: `ParticleSource.emit_record` tuples of the sources that emit this tick (device-side sources)."""
+        arr = (ScSource * len(records))(*[ScSource(*r) for r in records])
+        self._ck(self._L.sc_emit_particles(self._h, arr, len(records), int(max_particles)))
 
     def particle_count(self) -> int:
         n = C.c_int64()
@@ -424,6 +438,9 @@ class Context:
     def launch_count(self) -> int:
         return int(self._L.sc_launch_count(self._h))
 
+    def sync_count(self) -> int:
+        return int(self._L.sc_sync_count(self._h))
+
     def last_pair_count(self) -> int:
         n = C.c_int64()
         self._ck(self._L.sc_last_pair_count(self._h, C.byref(n)))
@@ -431,6 +448,13 @@ class Context:
 
     def untiled_blocks(self) -> int:
         return int(self._L.sc_debug_untiled_blocks(self._h))
+
+
+def source_uniform(seed: int, tick: int, source_index: int, j: int) -> float:
+    """Element j of a source's counter stream (host arithmetic of the library, no GPU needed)."""
+    u = C.c_double()
+    load().sc_source_stream(C.c_uint64(seed), C.c_uint64(tick), C.c_uint32(source_index), C.c_uint64(j), C.byref(u))
+    return u.value
 
 
 def wire_bytes(wire_capacity: int) -> int:

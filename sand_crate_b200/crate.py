@@ -6,9 +6,10 @@ Same constructor (`Crate(world_config)`), same `physics_tick()`, same attributes
 but the tick itself runs as sm_100a CUDA kernels behind the C ABI of `include/sandcrate.h`.  There is no NumPy
 or CPU implementation of the step in this package: without the CUDA library and a B200 the constructor raises.
 
-What stays on the host (inputs of the GPU step, O(#bodies) / a handful of particles per tick):
-particle sources and rigid-body motion, which consume the reference's global NumPy RNG / evaluate the YAML
-lambda strings (SURVEY.md section 2, rows "Rigid bodies" and "Particle sources").
+What stays on the host (inputs of the GPU step, O(#bodies) per tick): rigid-body motion, which evaluates the YAML
+lambda strings, and - in the reference-stream mode only - the particle sources, which consume the reference's global
+NumPy RNG (SURVEY.md section 2, rows "Rigid bodies" and "Particle sources").  In the counter mode the sources run on
+the device (`sc_emit_particles`) and a tick never waits for the GPU.
 
 Modes (keyword-only, the defaults reproduce the reference bit for bit):
   precision  "f64"   fp64 kernels, reference summation orders        | "mixed"  fp64 positions, fp32 forces
@@ -220,6 +221,8 @@ class Crate:
             self.debug_timer.update(self._ctx.profile_read())
 
     def create_new_particles(self) -> None:  # crate.py:138-147
+        if self.noise != "reference":
+            return self._emit_on_device()
         for source in self.particle_sources:
             if source.active_ticks <= self.tick:
                 continue
@@ -230,6 +233,25 @@ class Crate:
                 self._ctx.append_particles(new_pos, new_vel)
                 self._count = self.particle_count + len(new_pos)
                 self._cache = {}
+
+    def _emit_on_device(self) -> None:
+        """Production mode: the emission counts come from the counter stream (host arithmetic only), the particles
+        are generated, clamped to max_particles and appended by the device - no synchronisation (the reference-stream
+        path above has to know the live count, which costs a device round trip per tick while sources are active)."""
+        records = []
+        for index, source in enumerate(self.particle_sources):
+            if source.active_ticks <= self.tick:
+                continue
+            count = source.counter_count(_lib.source_uniform(self._noise_seed, self.tick, index, 0), self.dt)
+            if count:
+                records.append(source.emit_record(index, count))
+        if records:
+            self._ensure_capacity(int(self.max_particles))   # a no-op after the first call: capacity = max_particles
+            self._push_params()
+            self._ctx.set_tick(self.tick)
+            self._ctx.emit_particles(records, int(self.max_particles))
+            self._count = None
+            self._cache = {}
 
     def apply_bodies_velocity(self) -> None:  # crate.py:363-365
         for body in self.rigid_bodies:

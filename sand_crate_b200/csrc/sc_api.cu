@@ -93,6 +93,7 @@ struct sc_ctx {
     WireHeader *send_lo = nullptr, *send_hi = nullptr;  // the send buffers of the last sc_dist_pack (re-armed by unpack)
     unsigned push_toggle = 0;
     int64_t launches = 0;
+    int64_t syncs = 0;        // host waits on the stream (cudaStreamSynchronize) issued by this context's entry points
     bool profiling = false;
     std::vector<ProfEvent> pending;
     std::vector<cudaEvent_t> pool;
@@ -100,10 +101,13 @@ struct sc_ctx {
     double prof_ms[SC_PROFILE_SLOTS] = {0};
 };
 
+__global__ void k_end_tick(Counters *cnt, const uint32_t *total) { cnt->n = *total; }
+
 static int fail(sc_ctx *c, const std::string &m) {
     if (c) c->err = m; else g_create_error = m;
     return 1;
 }
+static cudaError_t stream_sync(sc_ctx *c) { c->syncs++; return cudaStreamSynchronize(c->stream); }
 #define CK(call)                                                                                        \
     do {                                                                                                \
         cudaError_t e_ = (call);                                                                        \
@@ -176,7 +180,7 @@ struct ProfScope {
 
 static int prof_flush(sc_ctx *ctx) {
     if (ctx->pending.empty()) return 0;
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (auto &p : ctx->pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, p.e0, p.e1);
@@ -469,8 +473,6 @@ extern "C" int sc_set_tick(sc_ctx *ctx, uint64_t tick) {
     return 0;
 }
 
-__global__ void k_end_tick(Counters *cnt, const uint32_t *total) { cnt->n = *total; }
-
 static int sync_count(sc_ctx *ctx) {
     if (ctx->carry_count) {  // a step ran since cnt->n was last written: its scan total is the live count
         ProfScope ps(ctx, SLOT_END);
@@ -480,7 +482,7 @@ static int sync_count(sc_ctx *ctx) {
     if (ctx->n_exact) return 0;
     Counters h;
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     ctx->n_host = h.n;
     ctx->n_exact = true;
     return 0;
@@ -508,7 +510,7 @@ static int upload_particles(sc_ctx *ctx, const double *pos, const double *vel, i
     ctx->next_uid += (uint32_t)n;
     const uint32_t newn = (uint32_t)(at + n);
     CK(cudaMemcpyAsync(&ctx->cnt->n, &newn, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // host buffers are borrowed for the duration of the call only
+    CK(stream_sync(ctx));  // host buffers are borrowed for the duration of the call only
     ctx->n_host = at + n;
     ctx->n_exact = true;
     ctx->rank_valid = false;
@@ -538,7 +540,7 @@ extern "C" int sc_set_state_uids(sc_ctx *ctx, const double *pos, const double *v
     }
     CKR(sc_set_state(ctx, pos, vel, n));
     if (n) CK(cudaMemcpyAsync(ctx->uid_cur, uid, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     ctx->next_uid = top + 1;
     return 0;
 }
@@ -552,6 +554,57 @@ extern "C" int sc_append_particles(sc_ctx *ctx, const double *pos, const double 
     if (ctx->n_host + n > ctx->cap) return fail(ctx, "sc_append_particles: capacity exceeded");
     ctx->srt_valid = false; ctx->lists_valid = false;  // (appended rows sit behind the sorted ones: rows_valid stays)
     return upload_particles(ctx, pos, vel, ctx->n_host, n);
+}
+
+extern "C" uint64_t sc_source_stream(uint64_t seed, uint64_t tick, uint32_t source_index, uint64_t j, double *u) {
+    const uint64_t key = source_key(tick_key(seed, tick), source_index);
+    if (u) *u = source_uniform(key, j);
+    return key;
+}
+
+extern "C" int sc_emit_particles(sc_ctx *ctx, const sc_source *sources, int nsources, int64_t max_particles) {
+    if (!ctx || (nsources > 0 && !sources)) return fail(ctx, "sc_emit_particles: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->in_step) return fail(ctx, "sc_emit_particles: inside a split step");
+    if (nsources < 0 || nsources > SC_MAX_SOURCES) return fail(ctx, "sc_emit_particles: more than SC_MAX_SOURCES sources");
+    if (ctx->dist_on) return fail(ctx, "sc_emit_particles: strips support closed scenes only");
+    EmitParams E{};
+    E.nsrc = 0;
+    E.max_particles = (uint32_t)std::min<int64_t>(std::max<int64_t>(max_particles, 0), ctx->cap);
+    uint64_t total = 0;
+    const uint64_t tkey = tick_key(ctx->seed, ctx->tick);
+    for (int q = 0; q < nsources; ++q) {
+        if (sources[q].count <= 0) continue;
+        EmitSource &S = E.src[E.nsrc++];
+        S.px = sources[q].position_x; S.py = sources[q].position_y; S.radius = sources[q].radius;
+        S.vx = sources[q].velocity_x; S.vy = sources[q].velocity_y; S.vnoise = sources[q].velocity_noise;
+        S.key = source_key(tkey, sources[q].index);
+        S.n = (uint32_t)sources[q].count;
+        S.uid_base = ctx->next_uid + (uint32_t)total;   // identities advance by the DRAWN count; a clamp leaves a gap
+        total += S.n;
+    }
+    if (!E.nsrc) return 0;
+    if ((uint64_t)ctx->next_uid + total >= (uint64_t)SC_GHOST_BIT)
+        return fail(ctx, "particle identities exhausted (2^31 particles created in this context)");
+    if (ctx->carry_count) {  // no force kernel ran since the last search: the count still sits in the scan total
+        ProfScope ps(ctx, SLOT_END);
+        k_end_tick<<<1, 1, 0, ctx->stream>>>(ctx->cnt, ctx->cell_start + ctx->grid.ncells);
+        ctx->carry_count = false;
+    }
+    {
+        ProfScope ps(ctx, SLOT_IO);
+        if (ctx->precision == SC_PRECISION_F64)
+            CK(launch_pdl(k_emit<double>, dim3(1), dim3(SC_BLOCK), ctx->stream, ctx->cnt, E, ctx->pos_cur, (double2 *)ctx->vel_cur,
+                          ctx->uid_cur, (uint32_t)ctx->cap));
+        else
+            CK(launch_pdl(k_emit<float>, dim3(1), dim3(SC_BLOCK), ctx->stream, ctx->cnt, E, ctx->pos_cur, (float2 *)ctx->vel_cur,
+                          ctx->uid_cur, (uint32_t)ctx->cap));
+    }
+    ctx->next_uid += (uint32_t)total;
+    ctx->n_host = std::min<int64_t>(ctx->n_host + (int64_t)total, ctx->cap);  // an upper bound: the clamp happened on the device
+    ctx->n_exact = false;
+    ctx->srt_valid = false; ctx->lists_valid = false; ctx->rank_valid = false;
+    return 0;
 }
 
 extern "C" int sc_host_alloc(size_t bytes, void **out) {
@@ -586,7 +639,7 @@ static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot, bool p
     unsigned long long *&desc = pre_cleared ? ctx->bsum : ctx->bsum2;
     size_t &cap = pre_cleared ? ctx->bsum_cap : ctx->bsum2_cap;
     if ((size_t)nb + 2 > cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         if (desc) CK(cudaFree(desc));
         CKR(dev_alloc(ctx, &desc, (size_t)nb + 2));
         cap = (size_t)nb + 2;
@@ -603,7 +656,7 @@ static int exclusive_scan(sc_ctx *ctx, uint32_t *a, uint32_t n, int slot, bool p
 static int build_rank_map(sc_ctx *ctx, const uint32_t *uid, const uint32_t *n_ptr) {
     const size_t need = (size_t)ctx->next_uid + 2;
     if (need > ctx->uid_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         if (ctx->rank_of_uid) CK(cudaFree(ctx->rank_of_uid));
         size_t cap = need * 2 > (size_t)ctx->cap + 2 ? need * 2 : (size_t)ctx->cap + 2;
         CKR(dev_alloc(ctx, &ctx->rank_of_uid, cap));
@@ -839,7 +892,7 @@ extern "C" int sc_step_begin(sc_ctx *ctx, int64_t *n_particles, int64_t *n_pairs
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&total, ctx->cell_start + ctx->grid.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost,
                        ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     if (n_particles) *n_particles = total;
     if (n_pairs) *n_pairs = h.n_pairs;
     return 0;
@@ -854,7 +907,7 @@ extern "C" int sc_step_finish(sc_ctx *ctx, const double *noise) {
         if (!noise) return fail(ctx, "sc_step_finish: SC_NOISE_HOST needs the noise array");
         Counters h;
         CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         const size_t need = (size_t)h.n_pairs * 2;
         if (need > ctx->noise_cap) {
             if (ctx->noise_dev) CK(cudaFree(ctx->noise_dev));
@@ -869,14 +922,14 @@ extern "C" int sc_step_finish(sc_ctx *ctx, const double *noise) {
     }
     ctx->in_step = false;
     CKR(enqueue_forces(ctx, noise_off));
-    if (host_noise) CK(cudaStreamSynchronize(ctx->stream));  // `noise` is borrowed for the call only
+    if (host_noise) CK(stream_sync(ctx));  // `noise` is borrowed for the call only
     return 0;
 }
 
 extern "C" int sc_synchronize(sc_ctx *ctx) {
     if (!ctx) return fail(ctx, "sc_synchronize: NULL ctx");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     return 0;
 }
@@ -938,7 +991,7 @@ extern "C" int sc_get_state(sc_ctx *ctx, double *pos, double *vel, double *press
         }
         CK(cudaMemcpyAsync(pressure, ctx->stage1, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     return 0;
 }
@@ -957,7 +1010,7 @@ extern "C" int sc_get_uids(sc_ctx *ctx, uint32_t *uid, int64_t cap, int64_t *n_o
     { ProfScope ps(ctx, SLOT_IO);
       k_scatter_uid<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->uid_cur, ctx->rank_of_uid, (uint32_t *)ctx->stage1); }
     CK(cudaMemcpyAsync(uid, ctx->stage1, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     return 0;
 }
 
@@ -969,7 +1022,7 @@ static int tap_prologue(sc_ctx *ctx, const char *who, int64_t cap, int64_t *n_ou
     CKR(no_neighbors(ctx, who));
     uint32_t total = 0;
     CK(cudaMemcpyAsync(&total, ctx->cell_start + ctx->grid.ncells, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     if ((int64_t)total > cap) return fail(ctx, std::string(who) + ": buffer too small");
     *n_out = total;
     if (!ctx->rank_valid) {
@@ -989,7 +1042,7 @@ extern "C" int sc_get_search(sc_ctx *ctx, double *pos_search, int64_t *rows_sort
         { ProfScope ps(ctx, SLOT_IO);
           k_scatter_vec2<double2><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, uid, ctx->rank_of_uid, ctx->pos_srt, ctx->stage2); }
         CK(cudaMemcpyAsync(pos_search, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
     }
     if (rows_sorted || order) {
         long long *rows_d = (long long *)ctx->stage2, *order_d = rows_d + n;  // stage2 holds 2n 8-byte slots
@@ -997,7 +1050,7 @@ extern "C" int sc_get_search(sc_ctx *ctx, double *pos_search, int64_t *rows_sort
           k_tap_search<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->grid, ctx->pos_srt, uid, ctx->rank_of_uid, rows_d, order_d); }
         if (rows_sorted) CK(cudaMemcpyAsync(rows_sorted, rows_d, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         if (order) CK(cudaMemcpyAsync(order, order_d, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
     }
     CK(cudaGetLastError());
     return 0;
@@ -1018,10 +1071,10 @@ extern "C" int sc_get_neighbors(sc_ctx *ctx, int32_t *counts, int32_t *idx, int6
         { ProfScope ps(ctx, SLOT_IO);
           k_tap_lists<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, ctx->count_by_rank, ctx->list_sorted, idx_d); }
         CK(cudaMemcpyAsync(idx, idx_d, sizeof(int) * (size_t)n * SC_MAX_NEIGHBORS, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(stream_sync(ctx));
         CK(cudaFree(idx_d));
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1038,7 +1091,7 @@ extern "C" int sc_get_tension(sc_ctx *ctx, double *tension, int64_t cap) {
       else
           k_scatter_ps<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, sorted_uids(ctx), ctx->rank_of_uid, (const PS<float> *)ctx->ps, nullptr, ctx->stage2); }
     CK(cudaMemcpyAsync(tension, ctx->stage2, sizeof(double2) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1051,7 +1104,7 @@ extern "C" int sc_get_wall_counts(sc_ctx *ctx, int32_t *counts, int64_t cap) {
     { ProfScope ps(ctx, SLOT_IO);
       k_tap_wall_counts<<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(n_ptr, ctx->dp, ctx->walls, sorted_uids(ctx), ctx->rank_of_uid, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->wall_pre, (int *)ctx->stage1); }
     CK(cudaMemcpyAsync(counts, ctx->stage1, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1117,7 +1170,7 @@ extern "C" int sc_points_to_segments_distance(sc_ctx *ctx, const double *p, int6
       k_points_segments<<<blocks_for(P * S), SC_BLOCK, 0, ctx->stream>>>(dp, (uint32_t)P, ds, S, dn, dd); }
     if (nearest) CK(cudaMemcpyAsync(nearest, dn, sizeof(double) * 2 * (size_t)P * S, cudaMemcpyDeviceToHost, ctx->stream));
     if (dist) CK(cudaMemcpyAsync(dist, dd, sizeof(double) * (size_t)P * S, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaGetLastError());
     cudaFree(dp); cudaFree(ds); cudaFree(dn); cudaFree(dd);
     return 0;
@@ -1137,7 +1190,7 @@ extern "C" int sc_last_pair_count(sc_ctx *ctx, int64_t *n_pairs) {
     }
     Counters h;
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     *n_pairs = (int64_t)h.n_pairs;
     return 0;
 }
@@ -1199,7 +1252,7 @@ extern "C" int sc_get_monitor(sc_ctx *ctx, double *sum_dv, int64_t *n) {
     if (!ctx->monitor) return fail(ctx, "sc_get_monitor: sc_set_monitor(ctx, 1) has not been called");
     double h[8];
     CK(cudaMemcpyAsync(h, ctx->monitor, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     for (int q = 0; q < 6; ++q) sum_dv[q] = h[q];
     if (n) *n = (int64_t)h[6];
     return 0;
@@ -1226,6 +1279,7 @@ extern "C" int sc_profile_read(sc_ctx *ctx, int64_t *launches, double *ms, int s
 }
 extern "C" const char *sc_profile_name(int slot) { return (slot >= 0 && slot < SC_PROFILE_SLOTS) ? k_slot_names[slot] : ""; }
 extern "C" int64_t sc_launch_count(const sc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t sc_sync_count(const sc_ctx *ctx) { return ctx ? ctx->syncs : 0; }
 
 
 // ---- strip decomposition ------------------------------------------------------------------------------------
@@ -1311,7 +1365,7 @@ extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, u
                                                                             ctx->uid_cur, row0, (int)nrows, d_hist);
     }
     CK(cudaMemcpyAsync(hist, d_hist, sizeof(uint64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     CK(cudaFree(d_hist));
     return 0;
 }
@@ -1471,14 +1525,14 @@ extern "C" int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t
     ctx->srt_valid = false;
     Counters h;
     CK(cudaMemcpyAsync(&h, ctx->cnt, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     if (n_out) *n_out = h.n_tmp;
     if ((int64_t)h.n_tmp > cap) return fail(ctx, "sc_dist_get_owned: buffer too small");
     const size_t m = h.n_tmp;
     if (m && pos) CK(cudaMemcpyAsync(pos, ctx->stage2, sizeof(double2) * m, cudaMemcpyDeviceToHost, ctx->stream));
     if (m && vel) CK(cudaMemcpyAsync(vel, ctx->pos_srt, sizeof(double2) * m, cudaMemcpyDeviceToHost, ctx->stream));
     if (m && uid) CK(cudaMemcpyAsync(uid, ctx->stage1, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     return 0;
 }
 
@@ -1493,7 +1547,7 @@ extern "C" int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *
     WireHeader w[2] = {};
     if (send_lo_dev && ctx->dist.has_lo) CK(cudaMemcpyAsync(&w[0], send_lo_dev, sizeof(WireHeader), cudaMemcpyDeviceToHost, ctx->stream));
     if (send_hi_dev && ctx->dist.has_hi) CK(cudaMemcpyAsync(&w[1], send_hi_dev, sizeof(WireHeader), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(stream_sync(ctx));
     if (overflow) *overflow = (h.overflow || w[0].overflow || w[1].overflow || h.n > (uint32_t)ctx->cap) ? 1 : 0;
     if (too_far) *too_far = (w[0].too_far || w[1].too_far) ? 1 : 0;
     if (n_local) *n_local = h.n;

@@ -132,6 +132,16 @@ __host__ __device__ inline uint32_t pair_noise_bits(uint64_t tkey, uint32_t uid_
     const uint32_t a = uid_i & 0x7FFFFFFFu, b = uid_j & 0x7FFFFFFFu;
     return lowbias32((a * 0x9E3779B1u) ^ (b * 0x85EBCA77u) ^ ((uint32_t)tkey ^ (uint32_t)(tkey >> 32)));
 }
+// ---- counter-based particle sources (production mode; oracle/step_oracle.c restates it) ---------------------
+// Stream of source q at a tick: element j is u(j) = (mix64(source_key(tick_key, q) + (j + 1) * GOLDEN) >> 11) * 2^-53.
+// j = 0 feeds the host's binomial draw of the emission count; particle k uses j = 1 + 4 k + {0: x, 1: y, 2: vx, 3: vy}.
+__host__ __device__ inline uint64_t source_key(uint64_t tkey, uint32_t q) {
+    return mix64(tkey ^ (0xD1B54A32D192ED03ULL * (uint64_t)(q + 1u)));
+}
+__host__ __device__ inline double source_uniform(uint64_t skey, uint64_t j) {
+    return (double)(mix64(skey + (j + 1ull) * 0x9E3779B97F4A7C15ULL) >> 11) * (1.0 / 9007199254740992.0);
+}
+
 // the two uniforms as fp32 in [1, 2) (k / 65536 + 1): bits dropped straight into the mantissa, no int-to-float convert
 __device__ __forceinline__ void pair_noise_f32_1to2(uint32_t h, float &fx, float &fy) {
     fx = __uint_as_float(0x3F800000u | ((h >> 9) & 0x007FFF80u));

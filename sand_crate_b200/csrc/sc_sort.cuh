@@ -406,6 +406,48 @@ k_points_segments(const double2 *p, uint32_t P_, const double *seg, int S,
     nearest[2 * (size_t)t + 1] = cy;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// create_new_particles (crate.py:138-147) + ParticleSource.generate_particles (particle_source.py:17-24) on the device,
+// production mode: the emission count of each source was drawn on the host from the counter stream (no device data
+// needed); HOW MANY of them fit - min(n, max_particles - particle_count), with particle_count the count BEFORE this
+// tick's removal and after the earlier sources of this tick, exactly as the reference evaluates it - is decided here
+// from the device-resident count, so the tick needs no host round trip.  One block; sources emit a handful per tick.
+struct EmitSource { double px, py, radius, vx, vy, vnoise; unsigned long long key; uint32_t n, uid_base; };
+struct EmitParams { EmitSource src[SC_MAX_SOURCES]; int nsrc; uint32_t max_particles; };
+template <typename Real>
+__global__ void __launch_bounds__(SC_BLOCK)
+k_emit(Counters *cnt, const __grid_constant__ EmitParams E, double2 *pos, typename Vec2<Real>::type *vel, uint32_t *uid,
+       uint32_t cap) {
+    pdl_enter();
+    __shared__ uint32_t s_base[SC_MAX_SOURCES], s_cnt[SC_MAX_SOURCES];
+    if (threadIdx.x == 0) {
+        uint32_t P = cnt->n;
+        for (int q = 0; q < E.nsrc; ++q) {
+            const uint32_t room = E.max_particles > P ? E.max_particles - P : 0u;
+            uint32_t a = E.src[q].n < room ? E.src[q].n : room;
+            if (P + a > cap) { a = cap > P ? cap - P : 0u; cnt->overflow = 1u; }
+            s_base[q] = P; s_cnt[q] = a;
+            P += a;
+        }
+        cnt->n = P;
+    }
+    __syncthreads();
+    for (int q = 0; q < E.nsrc; ++q) {
+        const EmitSource &S = E.src[q];
+        for (uint32_t k = threadIdx.x; k < s_cnt[q]; k += blockDim.x) {
+            const double ux = source_uniform(S.key, 1ull + 4ull * k), uy = source_uniform(S.key, 2ull + 4ull * k);
+            const double wx = source_uniform(S.key, 3ull + 4ull * k), wy = source_uniform(S.key, 4ull + 4ull * k);
+            const uint32_t at = s_base[q] + k;
+            pos[at] = make_double2((ux - 0.5) * S.radius + S.px, (uy - 0.5) * S.radius + S.py);      // particle_source.py:21
+            typename Vec2<Real>::type v;                                                            // particle_source.py:22-23
+            v.x = (Real)(S.vx + (wx - 0.5) * S.vnoise);
+            v.y = (Real)(S.vy + (wy - 0.5) * S.vnoise);
+            vel[at] = v;
+            uid[at] = S.uid_base + k;
+        }
+    }
+}
+
 // min / max cell coordinates of an arbitrary point set (standalone detect_particle_collisions)
 __global__ void __launch_bounds__(SC_BLOCK)
 k_cell_bounds(const double2 *pos, uint32_t n, double d, int *bounds /* rmin rmax cmin cmax */) {

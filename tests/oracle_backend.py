@@ -63,6 +63,32 @@ class OracleContext:
         self.next_uid += len(pos)
         self.prs = np.zeros(len(self.pos))
 
+    def emit_particles(self, records, max_particles):
+        """sc_emit_particles: the oracle's restatement of the device-side sources.  Identities advance by the DRAWN
+        counts (a clamp leaves a gap), like the library's."""
+        if not records:
+            return
+        src = np.array([r[:6] for r in records], dtype=np.float64)
+        cnt = np.array([r[6] for r in records], dtype=np.int32)
+        idx = np.array([r[7] for r in records], dtype=np.uint32)
+        import ctypes as C
+        pos = np.zeros((int(cnt.sum()), 2))
+        vel = np.zeros((int(cnt.sum()), 2))
+        P = len(self.pos)
+        m = O.lib().oc_emit_counter(C.c_uint64(O.tick_key(self.seed, self.tick)), len(records), O._dp(src), O._ip(cnt),
+                                    idx.ctypes.data_as(C.POINTER(C.c_uint32)), P, int(max_particles), O._dp(pos), O._dp(vel))
+        uids, base, room = [], self.next_uid, max(int(max_particles) - P, 0)
+        for n in cnt:
+            a = min(int(n), room)
+            uids.append(np.arange(base, base + a, dtype=np.uint32))
+            base += int(n)
+            room -= a
+        self.next_uid = base
+        self.pos = np.vstack((self.pos, pos[:m]))
+        self.vel = np.vstack((self.vel, vel[:m]))
+        self.uid = np.concatenate([self.uid] + uids)
+        self.prs = np.zeros(len(self.pos))
+
     def particle_count(self):
         return len(self.pos)
 

@@ -140,3 +140,38 @@ def test_force_monitor_overlay_matches_reference(oracle_backend, name, last):
             got = np.array([crate.force_monitor.context_to_velocity[k] for k in crate_mod.FORCE_SECTIONS])
             assert np.allclose(got, g[f"monitor_t{tick}"], rtol=1e-11, atol=1e-15), tick
     assert "Forces" in crate.debug_prints and "tension" in crate.force_monitor.report()
+
+
+def test_binomial_inverse_cdf_against_scipy():
+    """The emission count of the counter-stream sources: Binomial(flow, dt) through its inverse CDF."""
+    from scipy.stats import binom
+    from sand_crate_b200.particle_source import binomial_inverse_cdf
+    rs = np.random.RandomState(5)
+    for trials, p in ((2000, 0.002), (7000, 0.002), (50, 0.3)):
+        u = rs.rand(3000)
+        got = np.array([binomial_inverse_cdf(x, trials, p) for x in u])
+        want = binom.ppf(u, trials, p).astype(int)
+        assert (got != want).mean() < 2e-3          # equal except where u sits within rounding of a CDF step
+        assert abs(got.mean() - trials * p) < 0.15 * np.sqrt(trials * p)
+    assert binomial_inverse_cdf(0.0, 10, 0.5) == 0 and binomial_inverse_cdf(1.0, 10, 0.5) == 10
+
+
+def test_counter_sources_host_protocol(oracle_backend):
+    """Production mode of the drop-in Crate (counter noise, device-side sources): the host protocol - counter-stream
+    emission counts, sc_emit_particles, body motion, step - against an end-to-end restatement on the oracle."""
+    from conftest import oracle_counter_run
+    world, _ = world_from_freerun("wave_machine")
+    crate = Crate(world, noise="counter", noise_seed=11)
+    for tick, pos, vel, prs in oracle_counter_run(world, 11, 60):
+        crate.physics_tick()
+        if tick % 20 == 0:
+            assert crate.particle_count == len(pos) > 0
+            assert np.array_equal(crate.particles, pos) and np.array_equal(crate.particle_velocities, vel)
+    # the max_particles clamp (crate.py:143): a tiny cap is reached and never exceeded
+    world2, _ = world_from_freerun("wave_machine")
+    world2.coefficients["max_particles"] = 100
+    crate = Crate(world2, noise="counter", noise_seed=11)
+    for tick, pos, vel, prs in oracle_counter_run(world2, 11, 30):
+        crate.physics_tick()
+    assert crate.particle_count == len(pos) == 100
+    assert np.array_equal(crate.particles, pos)
