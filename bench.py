@@ -268,7 +268,7 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="strip exchange: NCCL send/recv or "
                     "direct NVLink stores into the neighbor's symmetric-memory buffer")
-    ap.add_argument("--rebalance-every", type=int, default=0, help="strips: re-cut the partition every N ticks")
+    ap.add_argument("--rebalance-every", type=int, default=50, help="strips: re-cut the partition every N ticks (0 = never)")
     ap.add_argument("--mgpu-particles", type=int, default=2_000_000, help="particles per GPU when --gpus > 1")
     ap.add_argument("--cpu-particles", type=int, default=200_000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")

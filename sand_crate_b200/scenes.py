@@ -81,9 +81,9 @@ def box_fill(n: int, seed: int = 42, **overrides):
 
 
 def dam_break_wide(n: int, seed: int = 42, **overrides):
-    """BASELINE.json configs[4] / SURVEY.md section 8(d): the 64M dam break is a column half the box wide and the whole
-    box high (A ~ 0.5)."""
-    return dam_break(n, seed, width=0.5, height=1.0, **overrides)
+    """BASELINE.json configs[4] / SURVEY.md section 8(d): the 64M dam break is a column half the box wide and (almost)
+    the whole box high (A ~ 0.5; 0.98 keeps the top lattice row below the lid)."""
+    return dam_break(n, seed, width=0.5, height=0.98, **overrides)
 
 
 SCENES = {"dam_break": dam_break, "box_fill": box_fill, "dam_break_wide": dam_break_wide}
@@ -96,7 +96,7 @@ def scene_chunks(name: str, n: int, seed: int = 42, chunk: int = 4_000_000, **ov
     if name == "dam_break":
         d, lat = _dam_break_geometry(n, 0.4, 0.8)
     elif name == "dam_break_wide":
-        d, lat = _dam_break_geometry(n, 0.5, 1.0)
+        d, lat = _dam_break_geometry(n, 0.5, 0.98)
     elif name == "box_fill":
         d, lat = _box_fill_geometry(n)
     else:
