@@ -268,7 +268,9 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="strip exchange: NCCL send/recv or "
                     "direct NVLink stores into the neighbor's symmetric-memory buffer")
-    ap.add_argument("--rebalance-every", type=int, default=50, help="strips: re-cut the partition every N ticks (0 = never)")
+    ap.add_argument("--rebalance-every", type=int, default=250, help="strips: re-cut the partition every N ticks (0 = never); "
+                    "a re-cut drains the stream (histogram to the host, all-reduce), about half a millisecond")
+    ap.add_argument("--halo-rows", type=int, default=4)
     ap.add_argument("--mgpu-particles", type=int, default=2_000_000, help="particles per GPU when --gpus > 1")
     ap.add_argument("--cpu-particles", type=int, default=200_000)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
@@ -351,7 +353,7 @@ def main():
         world, chunks = scene_chunks(scene, n_total)
         dom = StripDomain(world, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
                           device=local_rank, stream=stream, transport=a.transport,
-                          rebalance_every=a.rebalance_every, chunks=chunks)
+                          rebalance_every=a.rebalance_every, chunks=chunks, halo_rows=a.halo_rows)
         ctx = dom.ctx
         step_fn = dom.physics_tick
 

@@ -223,6 +223,12 @@ int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *send_hi_dev
  * `halo_rows` rows per tick - the rows it hands over then travel as ordinary migrants of the next sc_dist_pack. */
 int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, uint64_t *hist);
 int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi);
+/* How far a migrant may land: far_lo / far_hi = the first row of the lower neighbor's strip / one past the last row of
+ * the upper neighbor's.  A particle that crosses a cut is handed to the adjacent rank only, so it must land inside that
+ * rank's strip; beyond it the too_far flag is raised.  Default reach: halo_rows past the cut (the round-1 rule), which
+ * is tighter than necessary - the wall jets of a 8 000-row dam break move 3 rows per tick.  Call again after
+ * sc_dist_set_rows when the neighbors' cuts move. */
+int sc_dist_set_reach(sc_ctx *ctx, int64_t far_lo, int64_t far_hi);
 /* like sc_set_state but with caller-chosen uids (global particle ids of a partitioned scene) */
 int sc_set_state_uids(sc_ctx *ctx, const double *pos, const double *vel, const uint32_t *uid, int64_t n);
 

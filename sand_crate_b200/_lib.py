@@ -89,6 +89,7 @@ SIGNATURES = {
     "sc_dist_status": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), _lp]),
     "sc_dist_row_histogram": (C.c_int, [_ctx, C.c_int64, C.c_int64, C.POINTER(C.c_uint64)]),
     "sc_dist_set_rows": (C.c_int, [_ctx, C.c_int64, C.c_int64]),
+    "sc_dist_set_reach": (C.c_int, [_ctx, C.c_int64, C.c_int64]),
     "sc_set_state_uids": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64]),
     "sc_set_monitor": (C.c_int, [_ctx, C.c_int]),
     "sc_get_monitor": (C.c_int, [_ctx, _dp, _lp]),
@@ -383,6 +384,9 @@ class Context:
 
     def dist_set_rows(self, row_lo: int, row_hi: int):
         self._ck(self._L.sc_dist_set_rows(self._h, int(row_lo), int(row_hi)))
+
+    def dist_set_reach(self, far_lo: int, far_hi: int):
+        self._ck(self._L.sc_dist_set_reach(self._h, int(far_lo), int(far_hi)))
 
     def dist_get_owned(self, want_vel=True, want_uid=True, reuse=False):
         """(pos, vel, uid) of the owned particles.  reuse=True: views of page-locked buffers, valid until the next

@@ -55,7 +55,8 @@ struct sc_ctx {
     BlockDesc *blk_desc = nullptr;    // mixed mode: per block of SC_TILE sorted particles, its three windows
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
-    uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
+    uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr;
+    SortKey *key_srt = nullptr;       // sort keys (x, identity, index) in cell order, arrival order inside a cell
     // The cell grid and the wall bitmaps are double buffered by tick parity: a tick's force kernel clears the OTHER set
     // for the next tick (end_of_tick, sc_common.cuh), so a tick does not open with a clearing launch.  cell_start /
     // wall_bits_* always point at the set of the last search (the taps read them).
@@ -92,6 +93,12 @@ struct sc_ctx {
     WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers (+ push completion counters)
     WireHeader *send_lo = nullptr, *send_hi = nullptr;  // the send buffers of the last sc_dist_pack (re-armed by unpack)
     unsigned push_toggle = 0;
+    // The unpack kernel waits for the neighbors' records, and nothing of the tick's first pass over the particles this
+    // rank already holds (walls, cell keys) depends on them: the unpack is therefore DEFERRED - recorded here by
+    // sc_dist_unpack[_flagged] and launched by the step after that pass, followed by a second, small pass over what it
+    // appended.  The neighbors' latency hides behind ~20 us of work instead of standing at the head of the tick.
+    struct { bool on = false; const void *recv_lo = nullptr, *flag_lo = nullptr, *recv_hi = nullptr, *flag_hi = nullptr;
+             uint32_t value = 0; } pend;
     int64_t launches = 0;
     int64_t syncs = 0;        // host waits on the stream (cudaStreamSynchronize) issued by this context's entry points
     bool profiling = false;
@@ -247,6 +254,7 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
 }
 
 static void refresh_wall_boxes(sc_ctx *ctx);
+static int flush_pending_unpack(sc_ctx *ctx);
 static int sync_count(sc_ctx *ctx);
 
 #define SC_DIST_ROW_SLACK 96
@@ -318,7 +326,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, (char **)&c->vel_cur, n * 2 * rs); rc |= dev_alloc(c, (char **)&c->vel_srt, n * 2 * rs);
     rc |= dev_alloc(c, &c->uid_cur, n); rc |= dev_alloc(c, &c->uid_srt, n);
     rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
-    rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
+    rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->key_srt, n);
     rc |= dev_alloc(c, &c->rel_srt, n);
     if (precision == SC_PRECISION_MIXED) {
         rc |= dev_alloc(c, &c->rec_srt, n);
@@ -351,7 +359,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_bufs[0], c->cell_bufs[1], c->bsum, c->bsum2, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
+                    c->cell_key_srt, c->slot, c->key_srt, c->cell_bufs[0], c->cell_bufs[1], c->bsum, c->bsum2, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wbits_cur[0], c->wbits_cur[1], c->wbits_srt[0], c->wbits_srt[1], c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy, c->monitor};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -703,7 +711,17 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         ProfScope ps(ctx, SLOT_PREPASS);
         CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
                       ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap));
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
+                      (const uint32_t *)nullptr));
+    }
+    if (ctx->pend.on) {  // strips: now the neighbors' records, then the same pass over just what they appended
+        CKR(flush_pending_unpack(ctx));
+        ProfScope ps(ctx, SLOT_PREPASS);
+        const int64_t m = 2LL * ctx->dist.cap;
+        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((m + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
+                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
+                      (const uint32_t *)&ctx->cnt->n_split));
     }
     CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
@@ -711,19 +729,20 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
             ProfScope ps(ctx, SLOT_PLACE);
             CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
                           (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
-                          (const uint32_t *)ctx->cell_start, ctx->tmpidx, (uint32_t)ctx->cap));
+                          (const uint32_t *)ctx->cell_start, (const double2 *)ctx->pos_cur, (const uint32_t *)ctx->uid_cur,
+                          ctx->key_srt, ctx->cell_key_srt, (uint32_t)ctx->cap));
         }
         ProfScope ps(ctx, SLOT_RANK_GATHER);
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_pdl(k_rank_gather<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
-                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, (float4 *)nullptr, (BlockDesc *)nullptr));
+                g, ctx->cell_start, ctx->key_srt, ctx->cell_key_srt, ctx->pos_cur, (const double2 *)ctx->vel_cur,
+                ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, (float4 *)nullptr, (BlockDesc *)nullptr));
         else
             CK(launch_pdl(k_rank_gather<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
-                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->rec_srt, ctx->blk_desc));
+                g, ctx->cell_start, ctx->key_srt, ctx->cell_key_srt, ctx->pos_cur, (const float2 *)ctx->vel_cur,
+                ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->rec_srt, ctx->blk_desc));
     }
     CK(cudaGetLastError());
     ctx->srt_valid = true;
@@ -1287,7 +1306,7 @@ static int dist_ready(sc_ctx *ctx, const char *who) {
     CKR(require_ready(ctx, who));
     if (!ctx->dist_on) return fail(ctx, std::string(who) + ": sc_dist_configure has not been called");
     if (ctx->in_step) return fail(ctx, std::string(who) + ": inside a split step");
-    return 0;
+    return flush_pending_unpack(ctx);
 }
 
 extern "C" int64_t sc_dist_wire_bytes(int64_t wire_capacity) {
@@ -1305,6 +1324,8 @@ extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_
         return fail(ctx, "sc_dist_configure: a strip must be at least 2 * halo_rows high");
     if (ctx->noise_mode == SC_NOISE_HOST) return fail(ctx, "sc_dist_configure: SC_NOISE_HOST is single-GPU only");
     ctx->dist.row_lo = row_lo; ctx->dist.row_hi = row_hi; ctx->dist.halo = halo_rows;
+    ctx->dist.far_lo = row_lo - halo_rows; ctx->dist.far_hi = row_hi + halo_rows;  // until sc_dist_set_reach says more
+    ctx->dist.reach_set = 0;
     ctx->dist.has_lo = rank > 0; ctx->dist.has_hi = rank < nranks - 1;
     ctx->dist.cap = (uint32_t)wire_capacity;
     if (!ctx->wire_dummy) {
@@ -1324,6 +1345,7 @@ extern "C" int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi) {
     if (ctx->dist.has_lo && ctx->dist.has_hi && row_hi - row_lo < 2 * (int64_t)ctx->dist.halo)
         return fail(ctx, "sc_dist_set_rows: a strip must be at least 2 * halo_rows high");
     ctx->dist.row_lo = row_lo; ctx->dist.row_hi = row_hi;
+    if (!ctx->dist.reach_set) { ctx->dist.far_lo = row_lo - ctx->dist.halo; ctx->dist.far_hi = row_hi + ctx->dist.halo; }
     // the restricted cell grid must still cover the strip, its halo and the wall-fix shift
     const long long need = ctx->dist.halo + 2;
     const long long g_lo = (long long)ctx->grid.row_min + 1, g_hi = (long long)ctx->grid.row_min + ctx->grid.nrows - 2;
@@ -1340,6 +1362,13 @@ extern "C" int sc_dist_set_rows(sc_ctx *ctx, int64_t row_lo, int64_t row_hi) {
             ctx->n_exact = false;
         }
     }
+    return 0;
+}
+
+extern "C" int sc_dist_set_reach(sc_ctx *ctx, int64_t far_lo, int64_t far_hi) {
+    CKR(dist_ready(ctx, "sc_dist_set_reach"));
+    if (far_lo > ctx->dist.row_lo || far_hi < ctx->dist.row_hi) return fail(ctx, "sc_dist_set_reach: the reach must contain the strip");
+    ctx->dist.far_lo = far_lo; ctx->dist.far_hi = far_hi; ctx->dist.reach_set = 1;
     return 0;
 }
 
@@ -1442,8 +1471,8 @@ extern "C" int sc_dist_pack_push(sc_ctx *ctx, void *send_lo_dev, void *peer_recv
                         peer_recv_hi_dev, peer_flag_hi_dev, true, value);
 }
 
-static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, const void *recv_hi,
-                          const void *flag_hi, uint32_t value) {
+static int launch_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, const void *recv_hi,
+                         const void *flag_hi, uint32_t value) {
     UnpackSide lo{ctx->dist.has_lo ? (const WireHeader *)recv_lo : nullptr, (const uint32_t *)flag_lo};
     UnpackSide hi{ctx->dist.has_hi ? (const WireHeader *)recv_hi : nullptr, (const uint32_t *)flag_hi};
     if (lo.hdr || hi.hdr) {
@@ -1461,6 +1490,32 @@ static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo,
                 ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1));
     }
     CK(cudaGetLastError());
+    return 0;
+}
+
+// a deferred unpack that the step has not consumed yet (somebody asks for the state between unpack and step)
+static int flush_pending_unpack(sc_ctx *ctx) {
+    if (!ctx->pend.on) return 0;
+    ctx->pend.on = false;
+    return launch_unpack(ctx, ctx->pend.recv_lo, ctx->pend.flag_lo, ctx->pend.recv_hi, ctx->pend.flag_hi, ctx->pend.value);
+}
+
+static bool defer_unpack() {
+    static int v = -1;  // SC_DIST_DEFER=0: developer switch, launch the unpack where it is called (A/B timing)
+    if (v < 0) { const char *e = getenv("SC_DIST_DEFER"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
+static int enqueue_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, const void *recv_hi,
+                          const void *flag_hi, uint32_t value) {
+    CKR(flush_pending_unpack(ctx));
+    if (defer_unpack()) {
+        ctx->pend.on = true;
+        ctx->pend.recv_lo = recv_lo; ctx->pend.flag_lo = flag_lo; ctx->pend.recv_hi = recv_hi; ctx->pend.flag_hi = flag_hi;
+        ctx->pend.value = value;
+    } else {
+        CKR(launch_unpack(ctx, recv_lo, flag_lo, recv_hi, flag_hi, value));
+    }
     // the live count (owned + ghosts) is only known on the device: launch over the whole capacity, kernels exit early
     ctx->n_host = ctx->cap;
     ctx->n_exact = false;

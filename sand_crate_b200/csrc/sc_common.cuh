@@ -76,7 +76,8 @@ struct WallParams {
 // device-resident counters, zeroed/updated on the stream (no host round trip in the step)
 struct Counters {
     uint32_t n;          // live particles at the start of the tick (= after the previous tick's removal)
-    uint32_t n_removed;  // removed this tick
+    uint32_t n_split;    // strips: the count before the neighbors' records were appended (k_dist_pack) = where the
+                         // second, small wall / key pass of the tick starts (see enqueue_search)
     uint32_t n_wall;     // particles touching a wall this tick
     uint32_t n_pairs;    // sum K_i (filled by the count kernel)
     uint32_t overflow;   // capacity problems seen on the device

@@ -27,8 +27,12 @@ struct __align__(8) WireRec { double px, py, vx, vy; uint32_t uid, kind; };  // 
 
 struct DistCfg {
     long long row_lo, row_hi;  // owned rows: row_lo <= floor(y / d) < row_hi
+    long long far_lo, far_hi;  // rows owned by the two neighbors: far_lo <= row < row_lo below, row_hi <= row < far_hi
+                               // above.  A migrant must land INSIDE its neighbor's strip (anything further would need a
+                               // second hop: the too_far flag); by default the reach is one halo.
     int halo;                  // rows
     int has_lo, has_hi;        // neighbors exist
+    int reach_set;             // far_lo / far_hi were given by the caller
     uint32_t cap;              // records per wire buffer
 };
 
@@ -86,7 +90,7 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
     pdl_enter();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
-    if (idx == 0) cnt->n = n_in;
+    if (idx == 0) { cnt->n = n_in; cnt->n_split = n_in; }
     uint32_t i = idx;
     if (R.cell_start) {
         uint32_t A = D.has_lo ? R.cell_start[R.cell_a] : 0u, B = D.has_hi ? R.cell_start[R.cell_b] : n_in;
@@ -107,10 +111,10 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
             if (below || above) {
                 const typename Vec2<Real>::type v = vel[i];
                 if (below) {
-                    if (row < D.row_lo - D.halo) lo.hdr->too_far = 1u;
+                    if (row < D.far_lo) lo.hdr->too_far = 1u;
                     wire_push(lo.hdr, lo.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
                 } else {
-                    if (row >= D.row_hi + D.halo) hi.hdr->too_far = 1u;
+                    if (row >= D.far_hi) hi.hdr->too_far = 1u;
                     wire_push(hi.hdr, hi.recs, D.cap, p, (double)v.x, (double)v.y, u, SC_WIRE_MIGRANT);
                 }
                 uid[i] = u | SC_GHOST_BIT;

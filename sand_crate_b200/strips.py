@@ -178,6 +178,7 @@ class StripDomain:
         self.ctx.set_state_uids(pos_mine, vel_mine, mine)
         del pos_mine, vel_mine, mine
         self.ctx.dist_configure(rank, world_size, self.row_lo, self.row_hi, halo_rows, self.wire_capacity)
+        self._push_reach()
         self.tick = 0
         # re-balancing: every `rebalance_every` ticks the per-row histogram is summed over the ranks (the scheme's
         # only collective) and the cuts then SLIDE towards the new equal-count positions by at most halo - 2 rows per
@@ -218,6 +219,11 @@ class StripDomain:
                 self.transport = "p2p" if self._symm is not None else "nccl"
         elif transport == "auto":
             self.transport = "nccl"
+
+    def _push_reach(self) -> None:
+        """A migrant is handed to the adjacent rank only: tell the device where that rank's strip ends."""
+        if hasattr(self.ctx, "dist_set_reach") and self.world_size > 1:
+            self.ctx.dist_set_reach(self.cuts[max(self.rank - 1, 0)], self.cuts[min(self.rank + 2, self.world_size)])
 
     def _on_stream(self):
         """Context manager: torch work issued inside is ordered on the context's launch stream."""
@@ -291,7 +297,6 @@ class StripDomain:
             t = torch.from_numpy(hist).to(dev)
             dist.all_reduce(t)
             t = t.cpu()
-        self._check_flags()
         self.target_cuts = cuts_from_histogram(t.numpy(), self._row0, self.world_size, self.halo_rows)
 
     def _slide_cuts(self) -> None:
@@ -307,6 +312,7 @@ class StripDomain:
             self.cuts = new
             self.row_lo, self.row_hi = new[self.rank], new[self.rank + 1]
             self.ctx.dist_set_rows(self.row_lo, self.row_hi)
+            self._push_reach()
 
     def physics_tick(self) -> None:
         self.ctx.set_tick(self.tick)
