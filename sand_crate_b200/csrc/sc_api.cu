@@ -55,8 +55,7 @@ struct sc_ctx {
     BlockDesc *blk_desc = nullptr;    // mixed mode: per block of SC_TILE sorted particles, its three windows
     void *vel_cur = nullptr, *vel_srt = nullptr;
     uint32_t *uid_cur = nullptr, *uid_srt = nullptr;
-    uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr;
-    SortKey *key_srt = nullptr;       // sort keys (x, identity, index) in cell order, arrival order inside a cell
+    uint32_t *cell_key = nullptr, *cell_key_srt = nullptr, *slot = nullptr, *tmpidx = nullptr;
     // The cell grid and the wall bitmaps are double buffered by tick parity: a tick's force kernel clears the OTHER set
     // for the next tick (end_of_tick, sc_common.cuh), so a tick does not open with a clearing launch.  cell_start /
     // wall_bits_* always point at the set of the last search (the taps read them).
@@ -326,7 +325,7 @@ extern "C" int sc_create(int device, int precision, int64_t capacity, void *stre
     rc |= dev_alloc(c, (char **)&c->vel_cur, n * 2 * rs); rc |= dev_alloc(c, (char **)&c->vel_srt, n * 2 * rs);
     rc |= dev_alloc(c, &c->uid_cur, n); rc |= dev_alloc(c, &c->uid_srt, n);
     rc |= dev_alloc(c, &c->cell_key, n); rc |= dev_alloc(c, &c->cell_key_srt, n);
-    rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->key_srt, n);
+    rc |= dev_alloc(c, &c->slot, n); rc |= dev_alloc(c, &c->tmpidx, n);
     rc |= dev_alloc(c, &c->rel_srt, n);
     if (precision == SC_PRECISION_MIXED) {
         rc |= dev_alloc(c, &c->rec_srt, n);
@@ -359,7 +358,7 @@ extern "C" void sc_destroy(sc_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pos_cur, c->pos_srt, c->vel_cur, c->vel_srt, c->uid_cur, c->uid_srt, c->cell_key,
-                    c->cell_key_srt, c->slot, c->key_srt, c->cell_bufs[0], c->cell_bufs[1], c->bsum, c->bsum2, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
+                    c->cell_key_srt, c->slot, c->tmpidx, c->cell_bufs[0], c->cell_bufs[1], c->bsum, c->bsum2, c->rel_srt, c->rec_srt, c->blk_desc, c->ps, c->pair_j, c->pair_n, c->pair_off, c->pair_cnt,
                     c->wbits_cur[0], c->wbits_cur[1], c->wbits_srt[0], c->wbits_srt[1], c->wall_slot_cur, c->wall_slot_srt, c->wall_pre, c->cnt,
                     c->rank_of_uid, c->count_by_rank, c->list_sorted, c->noise_dev, c->stage2, c->stage1, c->wire_dummy, c->monitor};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -729,20 +728,19 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
             ProfScope ps(ctx, SLOT_PLACE);
             CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
                           (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
-                          (const uint32_t *)ctx->cell_start, (const double2 *)ctx->pos_cur, (const uint32_t *)ctx->uid_cur,
-                          ctx->key_srt, ctx->cell_key_srt, (uint32_t)ctx->cap));
+                          (const uint32_t *)ctx->cell_start, ctx->tmpidx, (uint32_t)ctx->cap));
         }
         ProfScope ps(ctx, SLOT_RANK_GATHER);
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_pdl(k_rank_gather<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                g, ctx->cell_start, ctx->key_srt, ctx->cell_key_srt, ctx->pos_cur, (const double2 *)ctx->vel_cur,
-                ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, (float4 *)nullptr, (BlockDesc *)nullptr));
+                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const double2 *)ctx->vel_cur,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (double2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, (float4 *)nullptr, (BlockDesc *)nullptr));
         else
             CK(launch_pdl(k_rank_gather<float>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
-                g, ctx->cell_start, ctx->key_srt, ctx->cell_key_srt, ctx->pos_cur, (const float2 *)ctx->vel_cur,
-                ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
-                ctx->uid_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->rec_srt, ctx->blk_desc));
+                g, ctx->cell_start, ctx->tmpidx, ctx->cell_key, ctx->pos_cur, (const float2 *)ctx->vel_cur,
+                ctx->uid_cur, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->pos_srt, ctx->rel_srt, (float2 *)ctx->vel_srt,
+                ctx->uid_srt, ctx->cell_key_srt, ctx->wall_bits_srt, ctx->wall_slot_srt, ctx->rec_srt, ctx->blk_desc));
     }
     CK(cudaGetLastError());
     ctx->srt_valid = true;

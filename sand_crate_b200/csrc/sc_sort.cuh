@@ -189,81 +189,60 @@ k_scan_lookback(uint32_t *a, uint32_t n, unsigned long long *desc,
 
 // ------------------------------------------------------------------------------------------------------------
 // K2: counting-sort placement.  The arrival slot inside a cell came from an atomic, so the order inside a cell
-// is arbitrary here; k_rank_gather makes it deterministic.  What is placed is the particle's whole SORT KEY - x, identity,
-// index - plus, in a second array, its cell: the ranking pass then reads its cell-mates' keys from ADJACENT slots
-// (coalesced, no pointer chasing through an index array into the position and identity arrays), and finds the ends of
-// its cell by comparing neighbouring cell entries instead of looking the cell's boundaries up.
-struct __align__(16) SortKey { double x; uint32_t uid, i; };
+// is arbitrary here; k_rank_gather makes it deterministic.
 #define SC_PLACE_ILP 4
 __global__ void __launch_bounds__(SC_BLOCK)
 k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
-        const uint32_t *cell_start, const double2 *pos, const uint32_t *uid,
-        SortKey *key_srt, uint32_t *cell_key_srt, uint32_t cap) {
+        const uint32_t *cell_start, uint32_t *tmpidx, uint32_t cap) {
     pdl_enter();
     const uint32_t n = cnt->n < cap ? cnt->n : cap;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
-    uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP], id[SC_PLACE_ILP];
-    double x[SC_PLACE_ILP];
+    uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP];
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u) {
         const uint32_t i = i0 + u * SC_BLOCK;
         c[u] = SC_INVALID_CELL;
-        if (i < n) { c[u] = cell_key[i]; sl[u] = slot[i]; x[u] = pos[i].x; id[u] = uid[i]; }
+        if (i < n) { c[u] = cell_key[i]; sl[u] = slot[i]; }
     }
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u)
         if (c[u] != SC_INVALID_CELL) st[u] = cell_start[c[u]];
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u)
-        if (c[u] != SC_INVALID_CELL) {
-            SortKey k;
-            k.x = x[u]; k.uid = id[u]; k.i = i0 + u * SC_BLOCK;
-            key_srt[st[u] + sl[u]] = k;
-            cell_key_srt[st[u] + sl[u]] = c[u];
-        }
-}
-
-// (x, identity) order inside a cell: x ascending (NaN last, like np.lexsort), ties by identity (lexsort is stable and
-// original index order == uid order); bit 31 of a uid only marks a ghost copy
-__device__ __forceinline__ uint32_t key_before(const SortKey &a, const SortKey &me) {
-    return (x_less(a.x, me.x) || (!x_less(me.x, a.x) && (a.uid & 0x7FFFFFFFu) < (me.uid & 0x7FFFFFFFu))) ? 1u : 0u;
+        if (c[u] != SC_INVALID_CELL) tmpidx[st[u] + sl[u]] = i0 + u * SC_BLOCK;
 }
 
 // K3: rank inside the cell by (x, uid) and gather the particle record to its final sorted position.
 // Produces exactly np.lexsort((x, floor(y / d))) (collision_detector.py:127) as the concatenation of cells.
-// Thread t holds the key that the placement left in slot t; its cell-mates are the adjacent slots with the same cell.
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
-k_rank_gather(Grid g, const uint32_t *cell_start, const SortKey *key_srt,
-              const uint32_t *cell_key_s, const double2 *pos,
-              const typename Vec2<Real>::type *vel,
+k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
+              const uint32_t *cell_key, const double2 *pos,
+              const typename Vec2<Real>::type *vel, const uint32_t *uid,
               const uint32_t *wall_bits, const uint32_t *wall_slot,
               double2 *pos_s, float2 *rel_s,
               typename Vec2<Real>::type *vel_s, uint32_t *uid_s,
-              uint32_t *wall_bits_s,
+              uint32_t *cell_key_s, uint32_t *wall_bits_s,
               uint32_t *wall_slot_s, SearchRec *rec_s, BlockDesc *desc) {
     pdl_enter();
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const SortKey me = key_srt[t];
-    const uint32_t c = cell_key_s[t];
-    const uint32_t i = me.i;
-    // the rest of the record: independent gathers, issued before the ranking walk needs anything
-    const double py = pos[i].y;
-    const typename Vec2<Real>::type v = vel[i];
-    const bool touching = (wall_bits[i >> 5] >> (i & 31)) & 1u;
-    uint32_t rank = 0, left = 0;
-    for (uint32_t m = t; m > 0u;) {
-        --m;
-        if (cell_key_s[m] != c) break;
-        ++left;
-        rank += key_before(key_srt[m], me);
+    const uint32_t i = tmpidx[t];
+    const uint32_t c = cell_key[i];
+    const uint32_t beg = cell_start[c], end = cell_start[c + 1];
+    const double2 p = pos[i];
+    const uint32_t u = uid[i];
+    const uint32_t um = u & 0x7FFFFFFFu;  // ties are broken by identity; bit 31 only marks a ghost copy
+    uint32_t rank = 0;
+    for (uint32_t m = beg; m < end; ++m) {
+        if (m == t) continue;
+        const uint32_t j = tmpidx[m];
+        const double xj = pos[j].x;
+        const uint32_t uj = uid[j] & 0x7FFFFFFFu;
+        rank += (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < um)) ? 1u : 0u;
     }
-    for (uint32_t m = t + 1u; m < n && cell_key_s[m] == c; ++m) rank += key_before(key_srt[m], me);
-    const uint32_t f = t - left + rank;
-    const double2 p = make_double2(me.x, py);
-    const uint32_t u = me.uid;
+    const uint32_t f = beg + rank;
     pos_s[f] = p;
     {   // cell-relative fp32 copy for the pair kernels' screening (see collect_neighbors)
         const uint32_t cr = c / (uint32_t)g.ncols, cc = c - cr * (uint32_t)g.ncols;
@@ -283,9 +262,10 @@ k_rank_gather(Grid g, const uint32_t *cell_start, const SortKey *key_srt,
             reinterpret_cast<uint4 *>(desc + f / SC_TILE)[1] =
                 make_uint4(cell_start[c + 2u], cell_start[c + nc + 2u], cell_start[c - nc + 2u], c);
     }
-    vel_s[f] = v;
+    vel_s[f] = vel[i];
     uid_s[f] = u;
-    if (touching) {
+    cell_key_s[f] = c;
+    if ((wall_bits[i >> 5] >> (i & 31)) & 1u) {
         wall_slot_s[f] = wall_slot[i];
         atomicOr(&wall_bits_s[f >> 5], 1u << (f & 31));
     }

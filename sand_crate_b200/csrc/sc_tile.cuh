@@ -32,9 +32,6 @@
 namespace sc {
 
 #define SC_TILE_CAP (5 * SC_TILE)              // staged particles per block (3 windows of ~SC_TILE + a few cells each)
-#ifndef SC_K4_MERGED
-#define SC_K4_MERGED 1                         // K4 screens a particle's four candidate ranges in one loop (see below)
-#endif
 #ifndef SC_K5_ROWS
 #define SC_K5_ROWS 6                           // pair-record slots of a block that K5 stages in shared memory
 #endif
@@ -178,39 +175,9 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         // range's cell row; DELTA = local - sorted index of the range's window.  count < 20 in the loop condition =
         // trim_collisions, collision_detector.py:91-93 (no `break`: it keeps the warp from reconverging).
         // (Ending the walk once a candidate is more than d away in x - rows are sorted by x - was measured: the extra
-        // predicate costs what the shorter walks save.)
-#if SC_K4_MERGED
-        // ONE loop over the four ranges, in list order: the warp runs max-over-lanes of the SUM of the four lengths
-        // instead of the sum of the four max-over-lanes (the lengths of a lane's ranges are nearly independent, so the
-        // sum varies much less across a warp than its parts: ~25 % fewer iterations), at the price of a few selects when
-        // a lane moves on to its next range.
-        {
-            int seg = 0;
-            uint32_t L = Ls + 1u, stop = b[1], step = 1u, code = 1u;
-            float by = me.y;
-            while (seg < 4 && count < SC_MAX_NEIGHBORS) {
-                if (L == stop) {
-                    ++seg;
-                    L = seg == 1 ? b[2] : (seg == 2 ? Ls - 1u : b[5] - 1u);
-                    stop = seg == 1 ? b[3] : (seg == 2 ? b[0] - 1u : b[4] - 1u);
-                    step = seg >= 2 ? 0xFFFFFFFFu : 1u;
-                    by = seg == 1 ? me.y - df : (seg == 2 ? me.y : me.y + df);
-                    code = seg == 1 ? 2u : (seg == 2 ? 1u : 0u);
-                } else {
-                    const SearchRec r = A.get(L);
-                    const float dx = fmaf(r.z - me.z, df, r.x - me.x), dy = r.y - by;
-                    const float qd = fmaf(dx, dx, dy * dy);
-                    /* qd > hi: surely farther than d (NaN too: the reference rejects NaN); qd < lo: surely inside */
-                    if (qd <= hi && (qd < lo || accept_exact(pos[s], pos[L - (code == 1u ? d0 : (code == 2u ? d1 : d2))], g.d,
-                                                             (int)code - 1, seg < 2))) {
-                        lst.set(count, L, code);
-                        ++count;
-                    }
-                    L += step;
-                }
-            }
-        }
-#else
+        // predicate costs what the shorter walks save.  ONE loop over the four ranges with a range-switch inside - fewer
+        // iterations per warp: max of sums instead of sum of maxes - was measured too: 71 us against 53, the switch
+        // makes every iteration divergent.)
 #define SC_TILE_RANGE(FIRST, STOP, STEP, BY, DR, DELTA, ASC)                                                     \
         {                                                                                                        \
             const float by = (BY);                                                                               \
@@ -230,7 +197,6 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         SC_TILE_RANGE(Ls - 1u, b[0] - 1u, 0xFFFFFFFFu, me.y, 0, d0, false)
         SC_TILE_RANGE(b[5] - 1u, b[4] - 1u, 0xFFFFFFFFu, me.y + df, -1, d2, false)
 #undef SC_TILE_RANGE
-#endif
         K = count;
     }
     // Records are SLOT-MAJOR inside the block's own region of the pair buffer: record k of thread t sits at
