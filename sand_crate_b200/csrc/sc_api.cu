@@ -286,6 +286,12 @@ static int refresh_dev_params(sc_ctx *ctx) {
     p.level = h.collider_noise_level; p.visc = h.viscosity; p.smooth = h.surface_smoothing;
     p.target = h.target_pressure; p.gx = h.gravity_x; p.gy = h.gravity_y;
     p.box_lo = -h.particle_radius; p.box_hi = 1 + h.particle_radius;     // crate.py:152
+    // fp32 constants of the mixed-precision kernels: the same operations, in the same order, the kernels used per thread
+    p.f_d = (float)p.d; p.f_inv_d = (float)(1.0 / p.d); p.f_amp = (float)(p.d * p.level);
+    p.f_band_hi = (p.f_d * p.f_d) * (1.0f + 4e-6f); p.f_band_lo = (p.f_d * p.f_d) * (1.0f - 4e-6f);
+    p.f_dt = (float)p.dt; p.f_dt_gx = (float)(p.dt * p.gx); p.f_dt_gy = (float)(p.dt * p.gy);
+    p.f_dt_amp = (float)(p.dt * p.amp); p.f_dt_visc = (float)(p.dt * p.visc);
+    p.f_smooth = (float)p.smooth; p.f_two_target = (float)(2 * p.target); p.f_ignored = (float)p.ignored;
     return 0;
 }
 
@@ -442,6 +448,13 @@ static void refresh_wall_boxes(sc_ctx *ctx) {
     };
     safe_rect(w.seg_box, w.S, w.safe_contact);
     safe_rect(w.pad_box, 2 * w.S, w.safe_ccd);
+    // fp32 copy, shrunk by far more than the fp32 rounding of a coordinate in [-1, 2] (6e-8) and of a movement
+    if (w.safe_ccd[0] < w.safe_ccd[1]) {
+        w.safe_ccd_f32[0] = (float)(w.safe_ccd[0] + 1e-6); w.safe_ccd_f32[1] = (float)(w.safe_ccd[1] - 1e-6);
+        w.safe_ccd_f32[2] = (float)(w.safe_ccd[2] + 1e-6); w.safe_ccd_f32[3] = (float)(w.safe_ccd[3] - 1e-6);
+    } else {
+        w.safe_ccd_f32[0] = 1.0f; w.safe_ccd_f32[1] = 0.0f; w.safe_ccd_f32[2] = 1.0f; w.safe_ccd_f32[3] = 0.0f;
+    }
 }
 
 extern "C" int sc_set_walls(sc_ctx *ctx, const double *segments, int S, const int32_t *body_len,
@@ -1479,12 +1492,12 @@ static int launch_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, 
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<double>, grid, dim3(SC_BLOCK), ctx->stream,
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
-                (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
+                (const uint32_t *)&ctx->cnt->n_split, (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
                 ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1));
         else
             CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<float>, grid, dim3(SC_BLOCK), ctx->stream,
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (float2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,
-                (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
+                (const uint32_t *)&ctx->cnt->n_split, (uint32_t)ctx->cap, &ctx->cnt->overflow, ctx->send_lo ? ctx->send_lo : ctx->wire_dummy,
                 ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1));
     }
     CK(cudaGetLastError());

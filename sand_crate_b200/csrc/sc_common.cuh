@@ -53,6 +53,11 @@ struct DevParams {
     double box_lo, box_hi;   // -r, 1 + r  (crate.py:152)
     int noise_mode;
     uint64_t tick_key;
+    // the fp32 kernels' constants, converted ONCE on the host (refresh_dev_params) with the same IEEE operations the
+    // kernels used to spend on them per thread - an fp64 reciprocal and half a dozen fp64 -> fp32 conversions per
+    // particle were ~5 % of the density kernel's instructions
+    float f_d, f_inv_d, f_amp /* d * level */, f_band_hi, f_band_lo /* d^2 (1 +- 4e-6): the fp32 screen's certain zone */;
+    float f_dt, f_dt_gx, f_dt_gy, f_dt_amp, f_dt_visc, f_smooth, f_two_target, f_ignored;
 };
 
 struct WallParams {
@@ -71,6 +76,7 @@ struct WallParams {
     // that lets the bulk of the liquid skip the per-segment loops altogether
     double safe_contact[4];
     double safe_ccd[4];
+    float safe_ccd_f32[4];  // safe_ccd shrunk by 1e-6: the mixed-precision kernel tests the movement in fp32 first
 };
 
 // device-resident counters, zeroed/updated on the stream (no host round trip in the step)

@@ -388,25 +388,46 @@ __device__ __forceinline__ void force_tail(uint32_t s, int K, Real p_i, Real tx,
         }
     }
 
-    const Real dt = (Real)P.dt;
+    const Real dt = sizeof(Real) == 4 ? (Real)P.f_dt : (Real)P.dt;
     Real vx = v0.x, vy = v0.y;
     if constexpr (kMonitor) { mpx = (double)vx; mpy = (double)vy; }
     if (K > 0) { vx += dt * tx; vy += dt * ty; }                       // F3, crate.py:352
     stage(0, (double)vx, (double)vy);
-    vx += (Real)(P.dt * P.gx); vy += (Real)(P.dt * P.gy);               // F4, crate.py:310
+    if constexpr (sizeof(Real) == 4) { vx += P.f_dt_gx; vy += P.f_dt_gy; }
+    else { vx += (Real)(P.dt * P.gx); vy += (Real)(P.dt * P.gy); }      // F4, crate.py:310
     stage(1, (double)vx, (double)vy);
     if (K + V > 0) {                                                     // F5, crate.py:297, 306
-        const Real c = (Real)(P.dt * P.amp);
+        const Real c = sizeof(Real) == 4 ? (Real)P.f_dt_amp : (Real)(P.dt * P.amp);
         vx += c * qx; vy += c * qy;
     }
     stage(2, (double)vx, (double)vy);
     {                                                                    // F6, crate.py:319-323
         Real ax = 0, ay = 0;
         visc(vx, vy, ax, ay);
-        const Real c = (Real)(P.dt * P.visc);
+        const Real c = sizeof(Real) == 4 ? (Real)P.f_dt_visc : (Real)(P.dt * P.visc);
         vx += c * ax; vy += c * ay;
     }
     stage(3, (double)vx, (double)vy);
+    // Mixed precision, the bulk of the liquid (no wall contact, and the movement's box - taken in fp32, against a safe
+    // rectangle shrunk by far more than fp32 rounding - stays clear of every padded segment): nothing of B1 / B2 applies,
+    // and the fp64 detour below (conversions, products, min / max, compares: ~40 instructions) is skipped.  The result
+    // is bit-identical to the general path's.
+    bool bulk = false;
+    if constexpr (sizeof(Real) == 4 && !kMonitor) {
+        if (V == 0) {
+            const float x0 = (float)ps.x, y0 = (float)ps.y;
+            const float x1 = fmaf((float)vx, P.f_dt, x0), y1 = fmaf((float)vy, P.f_dt, y0);
+            bulk = fminf(x0, x1) > W.safe_ccd_f32[0] && fmaxf(x0, x1) < W.safe_ccd_f32[1] &&
+                   fminf(y0, y1) > W.safe_ccd_f32[2] && fmaxf(y0, y1) < W.safe_ccd_f32[3];
+        }
+    }
+    if (bulk) {
+        R2 vq;
+        vq.x = vx; vq.y = vy;
+        vel_out[s] = vq;
+        pos_out[s] = make_double2(ps.x + P.dt * (double)vq.x, ps.y + P.dt * (double)vq.y);   // I, crate.py:361
+        return;
+    }
     double dvx = (double)vx, dvy = (double)vy;
     if (V > 0) {                                                         // B1, crate.py:245-259
         const double Nx = wnx / (double)V, Ny = wny / (double)V;

@@ -477,7 +477,7 @@ k_begin_tick(Counters *cnt, uint32_t *cell_count, uint32_t ncells, int carry_cou
     if (tid == 0) {
         if (carry_count) cnt->n = cell_count[ncells];
         if (cnt->n > cap) { cnt->n = cap; cnt->overflow = 1u; }
-        cnt->n_split = 0; cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0; cnt->n_untiled = 0;
+        cnt->n_wall = 0; cnt->n_pairs = 0; cnt->pair_cursor = 0; cnt->n_untiled = 0;
     }
     uint4 *c4 = reinterpret_cast<uint4 *>(cell_count);
     const uint32_t n4 = ncells / 4;

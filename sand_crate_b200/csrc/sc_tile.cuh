@@ -162,12 +162,12 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
                                                  const uint32_t (&b)[6], const Grid &g, const DevParams &P,
                                                  const double2 *pos, uint2 *pair_rec,
                                                  uint8_t *pair_cnt, PS<float> *ps_out) {
-    const float df = (float)g.d;
+    const float df = P.f_d;
     const uint32_t d0 = w.off[0] - w.base[0], d1 = w.off[1] - w.base[1], d2 = w.off[2] - w.base[2];
     int K = 0;
     SearchRec me = make_float4(0, 0, 0, 0);
     if (live) {
-        const float hi = (df * df) * (1.0f + 4e-6f), lo = (df * df) * (1.0f - 4e-6f);
+        const float hi = P.f_band_hi, lo = P.f_band_lo;
         const uint32_t Ls = s + d0;
         me = A.get(Ls);
         int count = 0;
@@ -205,8 +205,8 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
     if (!live) return;
     pair_cnt[s] = (uint8_t)K;
     const uint32_t uid_s = __float_as_uint(me.w);
-    const float inv_d = (float)(1.0 / P.d);
-    const float amp = (float)(P.d * P.level);
+    const float inv_d = P.f_inv_d;
+    const float amp = P.f_amp;
     float ax = 0, ay = 0, psum = 0;
     uint2 *out = pair_rec + (size_t)blockIdx.x * (SC_MAX_NEIGHBORS * SC_TILE) + threadIdx.x;
     for (int k = 0; k < K; ++k) {
@@ -235,7 +235,7 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
     }
     float p = 0;
     if (K > 0) {
-        const float pr = psum - (float)P.ignored;
+        const float pr = psum - P.f_ignored;
         p = (pr > 0 || pr != pr) ? pr : 0.0f;  // np.maximum(0, pr), crate.py:273
     }
     PS<float> o;
@@ -382,7 +382,7 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
     mbar_wait(bar, 0u);
     if (!live) return;
     const float p_i = me.p;
-    const float smooth = (float)P.smooth, two_target = (float)(2 * P.target);
+    const float smooth = P.f_smooth, two_target = P.f_two_target;
     float tx = 0, ty = 0;         // F3 sum
     float qx = 0, qy = 0;         // F5 sum
     float sum_vx = 0, sum_vy = 0;  // sum of neighbor velocities (F6)
