@@ -353,7 +353,8 @@ def main():
         world, chunks = scene_chunks(scene, n_total)
         dom = StripDomain(world, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
                           device=local_rank, stream=stream, transport=a.transport,
-                          rebalance_every=a.rebalance_every, chunks=chunks, halo_rows=a.halo_rows)
+                          rebalance_every=a.rebalance_every, chunks=chunks, halo_rows=a.halo_rows,
+                          check_every=0)   # the device flags are reported in the line (`strips`), not raised mid-run
         ctx = dom.ctx
         step_fn = dom.physics_tick
 
