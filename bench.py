@@ -391,8 +391,10 @@ def main():
                                           "rows": [int(dom.row_lo), int(dom.row_hi)], "mean_pairs": mean_pairs})
 
     # ---- N > 1: the same per-GPU workload on ONE GPU, inside this invocation, as the weak-scaling baseline ---------
+    # (only for box-fill: a dam break of 1/N the particles in the same box is a different column - fewer, larger
+    # particles, another hydrostatic load - not 1/N of the work)
     weak = None
-    if world_size > 1 and not a.no_weak_baseline:
+    if world_size > 1 and not a.no_weak_baseline and scene == "box_fill":
         if rank == 0:
             _, c1 = single_gpu_context(scene, n)
             for _ in range(a.relax + a.warmup):

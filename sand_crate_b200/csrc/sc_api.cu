@@ -1459,7 +1459,7 @@ static int enqueue_pack(sc_ctx *ctx, const char *who, void *send_lo_dev, void *s
     uint32_t *done = reinterpret_cast<uint32_t *>(ctx->wire_dummy + 3);  // "blocks done" counter of the fused kernel
     if (launch_n > 0) {
         ProfScope ps(ctx, SLOT_DIST_PACK);
-        const dim3 grid(blocks_for(launch_n)), block(SC_BLOCK);
+        const dim3 grid(std::min<unsigned>(blocks_for(launch_n), 2 * 148)), block(SC_BLOCK);  // grid-stride: few, fat blocks
         const bool pdl = dist_pdl_mask() & 1;
 #define SC_PACK(REAL, DIRECT)                                                                                        \
         CK(launch_maybe_pdl(pdl, k_dist_pack<REAL, DIRECT>, grid, block, ctx->stream, ctx->cnt, n_in, g, ctx->dist, R,   \
@@ -1490,7 +1490,7 @@ static int launch_unpack(sc_ctx *ctx, const void *recv_lo, const void *flag_lo, 
     UnpackSide hi{ctx->dist.has_hi ? (const WireHeader *)recv_hi : nullptr, (const uint32_t *)flag_hi};
     if (lo.hdr || hi.hdr) {
         ProfScope ps(ctx, SLOT_DIST_UNPACK);
-        const dim3 grid(blocks_for(ctx->dist.cap), 2);
+        const dim3 grid(std::min<unsigned>(blocks_for(ctx->dist.cap), 74), 2);  // grid-stride
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_maybe_pdl(dist_pdl_mask() & 4, k_dist_unpack<double>, grid, dim3(SC_BLOCK), ctx->stream,
                 lo, hi, value, ctx->dist.cap, ctx->pos_cur, (double2 *)ctx->vel_cur, ctx->uid_cur, &ctx->cnt->n,

@@ -100,17 +100,22 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
             double2 *pos, const typename Vec2<Real>::type *vel,
             uint32_t *uid, PackOut lo, PackOut hi, uint32_t *done, uint32_t value) {
     pdl_enter();
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
-    if (idx == 0) { cnt->n = n_in; cnt->n_split = n_in; }
-    uint32_t i = idx;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt->n = n_in; cnt->n_split = n_in; }
+    // the work list: [0, A) and [B, n_in) in zone mode, [0, n_in) otherwise; a FEW fat blocks walk it with a grid
+    // stride (every block ends with a system-scope fence in the direct mode: 1 500 thin blocks spent more time in
+    // fences than in packing)
+    uint32_t A = n_in, B = n_in;
     if (R.cell_start) {
-        uint32_t A = D.has_lo ? R.cell_start[R.cell_a] : 0u, B = D.has_hi ? R.cell_start[R.cell_b] : n_in;
+        A = D.has_lo ? R.cell_start[R.cell_a] : 0u;
+        B = D.has_hi ? R.cell_start[R.cell_b] : n_in;
         if (B > n_in) B = n_in;
         if (A > B) A = B;
-        if (idx == 0 && A + (n_in - B) > gridDim.x * blockDim.x) { lo.hdr->overflow = 1u; hi.hdr->overflow = 1u; }
-        i = idx < A ? idx : B + (idx - A);
     }
+    const uint32_t total = A + (n_in - B);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t i = idx < A ? idx : (idx < total ? B + (idx - A) : n_in);
     // decide (divergent), then reserve and write (warp-uniform control flow: wire_reserve needs all lanes)
     int kind_lo = -1, kind_hi = -1;  // record kind for the lower / upper neighbor, -1 = none
     uint32_t u = 0u;
@@ -142,6 +147,7 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
         const typename Vec2<Real>::type v = vel[i];
         if (kind_lo >= 0) wire_store(lo.hdr, lo.recs, D.cap, k_lo, p, (double)v.x, (double)v.y, u, (uint32_t)kind_lo);
         if (kind_hi >= 0) wire_store(hi.hdr, hi.recs, D.cap, k_hi, p, (double)v.x, (double)v.y, u, (uint32_t)kind_hi);
+    }
     }
     if constexpr (kDirect) {
         __threadfence_system();  // this block's records have reached the neighbor before it is counted as done
@@ -196,16 +202,17 @@ k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, d
     }
     const UnpackSide side = blockIdx.y ? hi : lo;
     if (!side.hdr) return;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (blockIdx.y ? c_hi : c_lo)) return;
-    const uint32_t k = base + (blockIdx.y ? c_lo : 0u) + i;
-    if (k >= cap) return;
-    const WireRec r = reinterpret_cast<const WireRec *>(side.hdr + 1)[i];
-    pos[k] = make_double2(r.px, r.py);
-    typename Vec2<Real>::type v;
-    v.x = (Real)r.vx; v.y = (Real)r.vy;
-    vel[k] = v;
-    uid[k] = r.kind == SC_WIRE_HALO ? (r.uid | SC_GHOST_BIT) : r.uid;
+    const uint32_t count = blockIdx.y ? c_hi : c_lo;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const uint32_t k = base + (blockIdx.y ? c_lo : 0u) + i;
+        if (k >= cap) return;
+        const WireRec r = reinterpret_cast<const WireRec *>(side.hdr + 1)[i];
+        pos[k] = make_double2(r.px, r.py);
+        typename Vec2<Real>::type v;
+        v.x = (Real)r.vx; v.y = (Real)r.vy;
+        vel[k] = v;
+        uid[k] = r.kind == SC_WIRE_HALO ? (r.uid | SC_GHOST_BIT) : r.uid;
+    }
 }
 
 // owned particles (no ghosts) compacted into staging arrays for readback; order is arbitrary, uids identify rows
