@@ -335,7 +335,10 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
 // instructions, its registers in flight and its barrier cost more than the gathers saved.  The bulk copy has none of
 // the three.
 template <bool kMonitor>
-__global__ void __launch_bounds__(SC_TILE, 4)
+#ifndef SC_K5_TILE_MINBLOCKS
+#define SC_K5_TILE_MINBLOCKS 4   // blocks per SM the register allocation is held to (4 = 64 registers)
+#endif
+__global__ void __launch_bounds__(SC_TILE, SC_K5_TILE_MINBLOCKS)
 k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallParams W, const BlockDesc *desc,
              const double2 *pos, const float2 *vel, const uint2 *pair_rec,
              const uint8_t *pair_cnt, const PS<float> *ps_in, const uint32_t *wall_bits, const uint32_t *wall_slot,
