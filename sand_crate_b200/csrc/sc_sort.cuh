@@ -26,21 +26,23 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
           uint32_t *cell_count, uint32_t *wall_bits, uint32_t *wall_slot,
           double2 *wall_pre, uint32_t cap, const uint32_t *first_ptr) {
     pdl_enter();
+    // first_ptr: the pass covers [*first_ptr, n) - the particles the strip exchange appended after the main pass ran
+    const uint32_t i0 = (first_ptr ? *first_ptr : 0u) + blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
+    // the positions are requested BEFORE the live count is known (any index below the capacity is readable): the count
+    // is itself a device-resident value, and waiting for it first put one more memory latency at the head of every thread
+    double2 p[SC_PREPASS_ILP];
+    uint32_t c[SC_PREPASS_ILP];
+#pragma unroll
+    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
+        const uint32_t i = i0 + u * SC_BLOCK;
+        if (i < cap) p[u] = pos[i];
+    }
     // the strip exchange appends with an atomic counter and only flags an overflow: every kernel bounds its indices by
     // the count, so the count itself must never exceed the arrays
     const uint32_t n = cnt->n < cap ? cnt->n : cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (cnt->n > cap) cnt->overflow = 1u;
         cnt->pair_cursor = 0; cnt->n_untiled = 0;  // consumed by this tick's density kernel
-    }
-    // first_ptr: the pass covers [*first_ptr, n) - the particles the strip exchange appended after the main pass ran
-    const uint32_t i0 = (first_ptr ? *first_ptr : 0u) + blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
-    double2 p[SC_PREPASS_ILP];
-    uint32_t c[SC_PREPASS_ILP];
-#pragma unroll
-    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
-        const uint32_t i = i0 + u * SC_BLOCK;
-        if (i < n) p[u] = pos[i];
     }
 #pragma unroll
     for (int u = 0; u < SC_PREPASS_ILP; ++u) {
@@ -195,15 +197,19 @@ __global__ void __launch_bounds__(SC_BLOCK)
 k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
         const uint32_t *cell_start, uint32_t *tmpidx, uint32_t cap) {
     pdl_enter();
-    const uint32_t n = cnt->n < cap ? cnt->n : cap;
     const uint32_t i0 = blockIdx.x * (SC_BLOCK * SC_PLACE_ILP) + threadIdx.x;
     uint32_t c[SC_PLACE_ILP], sl[SC_PLACE_ILP], st[SC_PLACE_ILP];
+    // keys and slots are requested before the live count is known (see k_prepass)
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u) {
         const uint32_t i = i0 + u * SC_BLOCK;
         c[u] = SC_INVALID_CELL;
-        if (i < n) { c[u] = cell_key[i]; sl[u] = slot[i]; }
+        if (i < cap) { c[u] = cell_key[i]; sl[u] = slot[i]; }
     }
+    const uint32_t n = cnt->n < cap ? cnt->n : cap;
+#pragma unroll
+    for (int u = 0; u < SC_PLACE_ILP; ++u)
+        if (i0 + u * SC_BLOCK >= n) c[u] = SC_INVALID_CELL;
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u)
         if (c[u] != SC_INVALID_CELL) st[u] = cell_start[c[u]];
@@ -233,6 +239,9 @@ k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
     const uint32_t beg = cell_start[c], end = cell_start[c + 1];
     const double2 p = pos[i];
     const uint32_t u = uid[i];
+    // the rest of the record: independent gathers, issued before the ranking walk so that they overlap its chain
+    const typename Vec2<Real>::type v_own = vel[i];
+    const bool touching = (wall_bits[i >> 5] >> (i & 31)) & 1u;
     const uint32_t um = u & 0x7FFFFFFFu;  // ties are broken by identity; bit 31 only marks a ghost copy
     uint32_t rank = 0;
     for (uint32_t m = beg; m < end; ++m) {
@@ -262,10 +271,10 @@ k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
             reinterpret_cast<uint4 *>(desc + f / SC_TILE)[1] =
                 make_uint4(cell_start[c + 2u], cell_start[c + nc + 2u], cell_start[c - nc + 2u], c);
     }
-    vel_s[f] = vel[i];
+    vel_s[f] = v_own;
     uid_s[f] = u;
     cell_key_s[f] = c;
-    if ((wall_bits[i >> 5] >> (i & 31)) & 1u) {
+    if (touching) {
         wall_slot_s[f] = wall_slot[i];
         atomicOr(&wall_bits_s[f >> 5], 1u << (f & 31));
     }

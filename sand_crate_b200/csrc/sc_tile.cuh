@@ -103,6 +103,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the same, made opaque to the compiler: on sm_100 a shared address is (cluster CTA rank << 24) + offset, and nvcc would
+// rather re-derive it (S2UR SR_CgaCtaId; UMOV; ULEA: three issue slots) inside a hot loop than keep it in a register
+__device__ __forceinline__ uint32_t smem_addr_pinned(const void *p) {
+    uint32_t a = smem_addr(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
 
 // the three windows of a `stride`-byte-per-particle array into shared memory at `dst` (W0 | W1 | W2); returns bytes
 __device__ __forceinline__ uint32_t stage_windows(const TileWindows &w, const void *src, uint32_t stride, uint32_t dst,
@@ -118,10 +125,20 @@ __device__ __forceinline__ uint32_t stage_windows(const TileWindows &w, const vo
 template <typename T> struct SmemAcc {
     uint32_t addr;
     __device__ __forceinline__ T get(uint32_t L) const;
+    // a CURSOR walks the staged array by byte address, so that the candidate loop's load needs no address arithmetic
+    static constexpr uint32_t kStep = (uint32_t)sizeof(T);
+    __device__ __forceinline__ uint32_t cursor(uint32_t L) const { return addr + L * kStep; }
+    __device__ __forceinline__ uint32_t index(uint32_t cur) const { return (cur - addr) / kStep; }
+    __device__ __forceinline__ T at(uint32_t cur) const;
 };
 template <> __device__ __forceinline__ float4 SmemAcc<float4>::get(uint32_t L) const {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr + L * 16u));
+    return v;
+}
+template <> __device__ __forceinline__ float4 SmemAcc<float4>::at(uint32_t cur) const {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cur));
     return v;
 }
 template <> __device__ __forceinline__ uint2 SmemAcc<uint2>::get(uint32_t L) const {
@@ -137,6 +154,10 @@ template <> __device__ __forceinline__ float2 SmemAcc<float2>::get(uint32_t L) c
 template <typename T> struct GmemAcc {
     const T *p;
     __device__ __forceinline__ T get(uint32_t L) const { return p[L]; }
+    static constexpr uint32_t kStep = 1u;
+    __device__ __forceinline__ uint32_t cursor(uint32_t L) const { return L; }
+    __device__ __forceinline__ uint32_t index(uint32_t cur) const { return cur; }
+    __device__ __forceinline__ T at(uint32_t cur) const { return p[cur]; }
 };
 // per-thread neighbor list, one column per thread; 16-bit entries when the indices are local (11 bits + row code)
 template <typename E, int kShift> struct TileList {
@@ -172,8 +193,9 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
         me = A.get(Ls);
         int count = 0;
         // FIRST .. STOP (exclusive) in local indices, walking by STEP; BY = y of this particle in the frame of the
-        // range's cell row; DELTA = local - sorted index of the range's window.  count < 20 in the loop condition =
-        // trim_collisions, collision_detector.py:91-93 (no `break`: it keeps the warp from reconverging).
+        // range's cell row; DELTA = local - sorted index of the range's window.  The walk is on a CURSOR (the staged
+        // record's shared-memory byte address), so the loop's load needs no address arithmetic: 15 instructions per
+        // rejected candidate instead of 20.
         // (Ending the walk once a candidate is more than d away in x - rows are sorted by x - was measured: the extra
         // predicate costs what the shorter walks save.  ONE loop over the four ranges with a range-switch inside - fewer
         // iterations per warp: max of sums instead of sum of maxes - was measured too: 71 us against 53, the switch
@@ -181,14 +203,21 @@ __device__ __forceinline__ void density_particle(const Acc &A, List lst, const T
 #define SC_TILE_RANGE(FIRST, STOP, STEP, BY, DR, DELTA, ASC)                                                     \
         {                                                                                                        \
             const float by = (BY);                                                                               \
-            for (uint32_t L = (FIRST); L != (STOP) && count < SC_MAX_NEIGHBORS; L += (STEP)) {                   \
-                const SearchRec r = A.get(L);                                                                    \
+            const uint32_t stop = A.cursor(STOP);                                                                \
+            /* trim_collisions (collision_detector.py:91-93): the 20th accept moves the cursor to the end of the */ \
+            /* range (no `break`, which keeps the warp from reconverging; no count test in the loop condition) */ \
+            if (count < SC_MAX_NEIGHBORS)                                                                        \
+            for (uint32_t cur = A.cursor(FIRST); cur != stop; cur += (STEP) * Acc::kStep) {                     \
+                const SearchRec r = A.at(cur);                                                                   \
                 const float dx = fmaf(r.z - me.z, df, r.x - me.x), dy = r.y - by;                                \
                 const float qd = fmaf(dx, dx, dy * dy);                                                          \
                 /* qd > hi: surely farther than d (NaN too: the reference rejects NaN); qd < lo: surely inside */ \
-                if (qd <= hi && (qd < lo || accept_exact(pos[s], pos[L - (DELTA)], g.d, (DR), (ASC)))) {         \
-                    lst.set(count, L, (uint32_t)((DR) + 1));                                                     \
-                    ++count;                                                                                     \
+                if (qd <= hi) {                                                                                  \
+                    const uint32_t L = A.index(cur);                                                             \
+                    if (qd < lo || accept_exact(pos[s], pos[L - (DELTA)], g.d, (DR), (ASC))) {                   \
+                        lst.set(count, L, (uint32_t)((DR) + 1));                                                 \
+                        if (++count == SC_MAX_NEIGHBORS) cur = stop - (STEP) * Acc::kStep;                       \
+                    }                                                                                            \
                 }                                                                                                \
             }                                                                                                    \
         }
@@ -310,7 +339,7 @@ k_density_tile(Counters *cnt, Grid g, DevParams P, const uint32_t *cell_start,
             b[2] = r1[0] + d1; b[3] = r1[3] + d1;
             b[4] = r2[0] + d2; b[5] = r2[3] + d2;
         }
-        density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr(s_rec)}, TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live,
+        density_particle<kNoise>(SmemAcc<SearchRec>{smem_addr_pinned(s_rec)}, TileList<uint16_t, 13>{s_list + threadIdx.x}, w, live,
                                  s, b, g, P, pos, pair_rec, pair_cnt, ps_out);
     } else {
         if (threadIdx.x == 0) atomicAdd(&cnt->n_untiled, 1u);  // rare; lets a test prove this path ran
@@ -389,11 +418,11 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
     float tx = 0, ty = 0;         // F3 sum
     float qx = 0, qy = 0;         // F5 sum
     float sum_vx = 0, sum_vy = 0;  // sum of neighbor velocities (F6)
-    const SmemAcc<float4> Aps{smem_addr(s_ps)};
-    const SmemAcc<float2> Avel{smem_addr(s_vel)};
-    const SmemAcc<uint2> Arec{smem_addr(s_pair) + threadIdx.x * 8u};
+    const SmemAcc<float4> Aps{smem_addr_pinned(s_ps)};
+    const SmemAcc<float2> Avel{smem_addr_pinned(s_vel)};
+    const SmemAcc<uint2> Arec{smem_addr_pinned(s_pair) + threadIdx.x * 8u};
     // one pair: F3 pass 2 (crate.py:347-353), F5 (301-306), F6's neighbor velocity sum (319-323), in list order
-    auto pair = [&](int k, uint2 r, auto get_ps, auto get_vel) {
+    auto pair = [&](uint2 r, auto get_ps, auto get_vel) {
         uint32_t L;
         float nx, ny;
         pair_decode(r, L, nx, ny);
@@ -406,8 +435,9 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
         const float ex = cc * nx, ey = cc * ny;
         const float ps_ = p_i + nb.x;
         const float fx = nx * ps_, fy = ny * ps_;
-        if (k == 0) { tx = ex; ty = ey; qx = fx; qy = fy; }
-        else { tx += ex; ty += ey; qx += fx; qy += fy; }
+        // (the sums start at +0: in fp32 0 + x == x, so the reference's "first row assigns" needs no special case here -
+        // unlike the fp64 kernel, where the bit pattern of -0 matters)
+        tx += ex; ty += ey; qx += fx; qy += fy;
         sum_vx += vj.x; sum_vy += vj.y;
     };
     // the loop is unswitched on the two block-uniform / rare conditions: staged or pass-through block, and record slots
@@ -416,13 +446,13 @@ k_force_tile(const uint32_t *n_ptr, DevParams P, const __grid_constant__ WallPar
     if (w.staged) {
         auto gp = [&](uint32_t L) { return Aps.get(L); };
         auto gv = [&](uint32_t L) { return Avel.get(L); };
-        for (int k = 0; k < Ks; ++k) pair(k, Arec.get((uint32_t)k * SC_TILE), gp, gv);
-        for (int k = SC_K5_ROWS; k < K; ++k) pair(k, my_rec[k * SC_TILE], gp, gv);
+        for (int k = 0; k < Ks; ++k) pair(Arec.get((uint32_t)k * SC_TILE), gp, gv);
+        for (int k = SC_K5_ROWS; k < K; ++k) pair(my_rec[k * SC_TILE], gp, gv);
     } else {
         auto gp = [&](uint32_t L) { const PS<float> g_ = ps_in[L]; return make_float4(g_.p, g_.sx, g_.sy, 0.0f); };
         auto gv = [&](uint32_t L) { return vel[L]; };
-        for (int k = 0; k < Ks; ++k) pair(k, Arec.get((uint32_t)k * SC_TILE), gp, gv);
-        for (int k = SC_K5_ROWS; k < K; ++k) pair(k, my_rec[k * SC_TILE], gp, gv);
+        for (int k = 0; k < Ks; ++k) pair(Arec.get((uint32_t)k * SC_TILE), gp, gv);
+        for (int k = SC_K5_ROWS; k < K; ++k) pair(my_rec[k * SC_TILE], gp, gv);
     }
     force_tail<float, kMonitor>(s, K, p_i, tx, ty, qx, qy, P, W, ps_own, v_own, touching, wall_slot, wall_pre, pos_out, vel_out,
                                 monitor, n_ptr, [&](float vx, float vy, float &ax, float &ay) {
