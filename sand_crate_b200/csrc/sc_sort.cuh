@@ -91,26 +91,10 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
         int row;
         c[u] = cell_of(g, p[u].x, p[u].y, row);
     }
-    // Arrival slots: one returning atomic per RUN of adjacent lanes with the same cell, not per particle.  The particles
-    // arrive in the previous tick's sorted order, so cell-mates are mostly adjacent lanes (1.8 per cell at rest density):
-    // the run's first lane reserves the run, every lane takes its place in it (~40 % fewer atomics; the kernel is bound by
-    // their round trip).
     uint32_t sl[SC_PREPASS_ILP];
-    const uint32_t lane = threadIdx.x & 31u;
 #pragma unroll
-    for (int u = 0; u < SC_PREPASS_ILP; ++u) {
-        const uint32_t key = c[u];
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const uint32_t heads = __ballot_sync(0xffffffffu, lane == 0u || key != prev);
-        const uint32_t upto = heads & (0xffffffffu >> (31u - lane));         // run heads at or below this lane
-        const uint32_t start = 31u - (uint32_t)__clz(upto);
-        const uint32_t above = lane == 31u ? 0u : heads & (0xffffffffu << (lane + 1u));
-        const uint32_t stop = above ? (uint32_t)__ffs(above) - 1u : 32u;
-        uint32_t base = 0u;
-        if (lane == start && key != SC_INVALID_CELL) base = atomicAdd(&cell_count[key], stop - start);
-        base = __shfl_sync(0xffffffffu, base, start);
-        sl[u] = base + (lane - start);
-    }
+    for (int u = 0; u < SC_PREPASS_ILP; ++u)
+        if (c[u] != SC_INVALID_CELL) sl[u] = atomicAdd(&cell_count[c[u]], 1u);
 #pragma unroll
     for (int u = 0; u < SC_PREPASS_ILP; ++u) {
         const uint32_t i = i0 + u * SC_BLOCK;
@@ -236,10 +220,6 @@ k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
 
 // K3: rank inside the cell by (x, uid) and gather the particle record to its final sorted position.
 // Produces exactly np.lexsort((x, floor(y / d))) (collision_detector.py:127) as the concatenation of cells.
-// Thread t holds the particle that the placement left in slot t.  Its cell-mates sit in the adjacent slots, i.e. mostly
-// in adjacent LANES, which have just loaded their own (x, uid): the ranking reads them with warp shuffles instead of two
-// more levels of dependent gathers (index -> position / identity) per mate.  Only the part of a cell that lies outside
-// the warp's 32 slots is gathered from memory.
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
@@ -253,47 +233,24 @@ k_rank_gather(Grid g, const uint32_t *cell_start, const uint32_t *tmpidx,
     pdl_enter();
     const uint32_t n = cell_start[g.ncells];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, wbase = t - lane;
-    if (wbase >= n) return;  // the whole warp is past the end
-    const bool live = t < n;
-    uint32_t i = 0, c = 0, beg = t, end = t + 1u, u = 0;
-    double2 p = make_double2(0, 0);
-    typename Vec2<Real>::type v_own;
-    v_own.x = 0; v_own.y = 0;
-    bool touching = false;
-    if (live) {
-        i = tmpidx[t];
-        c = cell_key[i];
-        p = pos[i];
-        u = uid[i];
-        // the rest of the record: independent gathers, in flight while the ranking runs
-        v_own = vel[i];
-        touching = (wall_bits[i >> 5] >> (i & 31)) & 1u;
-        beg = cell_start[c]; end = cell_start[c + 1];
-    }
+    if (t >= n) return;
+    const uint32_t i = tmpidx[t];
+    const uint32_t c = cell_key[i];
+    const uint32_t beg = cell_start[c], end = cell_start[c + 1];
+    const double2 p = pos[i];
+    const uint32_t u = uid[i];
+    // the rest of the record: independent gathers, issued before the ranking walk so that they overlap its chain
+    const typename Vec2<Real>::type v_own = vel[i];
+    const bool touching = (wall_bits[i >> 5] >> (i & 31)) & 1u;
     const uint32_t um = u & 0x7FFFFFFFu;  // ties are broken by identity; bit 31 only marks a ghost copy
-    auto before = [&](double xj, uint32_t uj) -> uint32_t {
-        return (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < um)) ? 1u : 0u;
-    };
-    // my cell inside this warp: lanes lo .. hi (slots of a cell are contiguous)
-    const uint32_t lo = beg > wbase ? beg - wbase : 0u, hi = (end < wbase + 32u ? end : wbase + 32u) - wbase - 1u;
     uint32_t rank = 0;
-    const uint32_t span = __reduce_max_sync(0xffffffffu, hi - lo);
-    for (uint32_t o = 1; o <= span; ++o) {  // warp-uniform trip count; every lane takes part in the shuffles
-        const double xl = __shfl_up_sync(0xffffffffu, p.x, o), xr = __shfl_down_sync(0xffffffffu, p.x, o);
-        const uint32_t ul = __shfl_up_sync(0xffffffffu, um, o), ur = __shfl_down_sync(0xffffffffu, um, o);
-        if (lane >= lo + o) rank += before(xl, ul);
-        if (lane + o <= hi) rank += before(xr, ur);
+    for (uint32_t m = beg; m < end; ++m) {
+        if (m == t) continue;
+        const uint32_t j = tmpidx[m];
+        const double xj = pos[j].x;
+        const uint32_t uj = uid[j] & 0x7FFFFFFFu;
+        rank += (x_less(xj, p.x) || (!x_less(p.x, xj) && uj < um)) ? 1u : 0u;
     }
-    if (live) {  // the rest of the cell, in the neighbouring warps' slots (cells that straddle a warp boundary)
-        const uint32_t e0 = end < wbase ? end : wbase;
-        for (uint32_t m = beg; m < e0; ++m) { const uint32_t j = tmpidx[m]; rank += before(pos[j].x, uid[j] & 0x7FFFFFFFu); }
-        for (uint32_t m = (beg > wbase + 32u ? beg : wbase + 32u); m < end; ++m) {
-            const uint32_t j = tmpidx[m];
-            rank += before(pos[j].x, uid[j] & 0x7FFFFFFFu);
-        }
-    }
-    if (!live) return;
     const uint32_t f = beg + rank;
     pos_s[f] = p;
     {   // cell-relative fp32 copy for the pair kernels' screening (see collect_neighbors)
