@@ -31,8 +31,7 @@ METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
 # algorithmic bytes per particle per kernel for the mixed layout (pos f64x2, vel f32x2, id, p, s,
 # cell id), each record moved once per kernel.  These are the figures `roofline.achieved` is computed from.
-SURVEY_BYTES = {"prepass_wall_key": 20, "place": 14, "sort_front": 34, "rank_gather": 56, "density": 28, "force_integrate": 60}
-# ("sort_front" = the pre-pass, the cell scan and the placement as one persistent kernel: 20 + 14 bytes)
+SURVEY_BYTES = {"prepass_wall_key": 20, "place": 14, "rank_gather": 56, "density": 28, "force_integrate": 60}
 DEFAULT_PARTICLES = 1_000_000
 
 

@@ -11,7 +11,7 @@ import os
 import subprocess
 import sys
 
-SLOT_OF = {"k_begin_tick": "clear", "k_sort_front": "sort_front", "k_prepass": "prepass_wall_key", "k_scan_lookback": "scan", "k_place": "place",
+SLOT_OF = {"k_begin_tick": "clear", "k_prepass": "prepass_wall_key", "k_scan_lookback": "scan", "k_place": "place",
            "k_rank_gather": "rank_gather", "k_density": "density", "k_force": "force_integrate",
            "k_dist_pack": "dist_pack", "k_dist_unpack": "dist_unpack", "k_emit": "io_scatter"}
 

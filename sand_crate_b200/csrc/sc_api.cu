@@ -18,11 +18,11 @@ static std::string g_create_error;
 
 enum Slot {
     SLOT_CLEAR = 0, SLOT_PREPASS, SLOT_SCAN, SLOT_PLACE, SLOT_RANK_GATHER, SLOT_DENSITY, SLOT_FORCE, SLOT_COUNT,
-    SLOT_RANKMAP, SLOT_IO, SLOT_END, SLOT_DIST_PACK, SLOT_DIST_PUSH, SLOT_DIST_UNPACK, SLOT_SORT_FRONT
+    SLOT_RANKMAP, SLOT_IO, SLOT_END, SLOT_DIST_PACK, SLOT_DIST_PUSH, SLOT_DIST_UNPACK
 };
 static const char *k_slot_names[SC_PROFILE_SLOTS] = {
     "clear", "prepass_wall_key", "scan", "place", "rank_gather", "density", "force_integrate", "count_neighbors",
-    "rank_map", "io_scatter", "end_tick", "dist_pack", "dist_push", "dist_unpack", "sort_front", ""};
+    "rank_map", "io_scatter", "end_tick", "dist_pack", "dist_push", "dist_unpack", "", ""};
 // NVTX range per launch, named after the section of the reference's tick the kernel replaces (the `debug_timer`
 // sections of crate.py:97-124, utils/timer.py:10-48) so a timeline reads like the reference's own Timer overlay
 static const char *k_slot_nvtx[SC_PROFILE_SLOTS] = {
@@ -31,8 +31,7 @@ static const char *k_slot_nvtx[SC_PROFILE_SLOTS] = {
     "Collisions + Colliders + Pressure + tension pass 1 (density kernel)",
     "tension, gravity, pressure, viscosity, wall_bounce, continuous_collision, integrate (force kernel)",
     "tap: neighbor counts", "readback: uid -> row map", "readback / upload", "end tick",
-    "strips: pack", "strips: NVLink push", "strips: unpack",
-    "Virtual Colliders + Collisions: walls, cell keys | cell scan | placement (one persistent kernel)", ""};
+    "strips: pack", "strips: NVLink push", "strips: unpack", "", ""};
 
 struct ProfEvent { int slot; cudaEvent_t e0, e1; };
 
@@ -100,8 +99,6 @@ struct sc_ctx {
     struct { bool on = false; const void *recv_lo = nullptr, *flag_lo = nullptr, *recv_hi = nullptr, *flag_hi = nullptr;
              uint32_t value = 0; } pend;
     int64_t launches = 0;
-    int front_blocks = 0;     // co-resident grid size of k_sort_front (0 = not yet asked)
-    bool front_pdl = true;    // k_sort_front is launched cooperatively AND with programmatic serialization while the driver lets us
     int64_t syncs = 0;        // host waits on the stream (cudaStreamSynchronize) issued by this context's entry points
     bool profiling = false;
     std::vector<ProfEvent> pending;
@@ -139,21 +136,6 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
-// Cooperative launch (all blocks co-scheduled: the kernel's grid barriers spin) that also asks for programmatic stream
-// serialization; if the driver refuses the combination the caller retries without the second attribute.
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_coop(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args &&...args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -258,7 +240,7 @@ static int setup_grid(sc_ctx *ctx, double d, int row_min, int row_max, int col_m
     }
     ctx->cell_start = ctx->cell_bufs[ctx->par];
     ctx->next_clean = false;  // a new grid: the next tick clears it itself
-    const size_t nb = (size_t)(g.ncells + SC_FRONT_TILE - 1) / SC_FRONT_TILE + 2;  // (the fused front's tiles are the smaller)
+    const size_t nb = (size_t)(g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
     const size_t nb2 = (size_t)(ctx->cap + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 2;
     const size_t needb = nb > nb2 ? nb : nb2;
     if (needb > ctx->bsum_cap) {
@@ -717,24 +699,6 @@ static int require_ready(sc_ctx *ctx, const char *who) {
     return 0;
 }
 
-static bool sort_fused() {
-    static int v = -1;  // SC_SORT_FUSED=0: developer switch, the three separate launches (A/B timing)
-    if (v < 0) { const char *e = getenv("SC_SORT_FUSED"); v = e ? atoi(e) : 1; }
-    return v != 0;
-}
-// blocks of k_sort_front that are guaranteed to be resident together (its grid barriers spin)
-static int front_blocks(sc_ctx *ctx) {
-    if (ctx->front_blocks > 0) return ctx->front_blocks;
-    int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sort_front<true>, SC_BLOCK, 0);
-    int per_sm2 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_sort_front<false>, SC_BLOCK, 0);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    per_sm = std::min(std::min(per_sm, per_sm2), 4);
-    ctx->front_blocks = std::max(1, per_sm * sms);
-    return ctx->front_blocks;
-}
-
 // remove -> walls -> keys -> sort -> gather
 template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
     const int64_t n = ctx->n_host;
@@ -748,65 +712,37 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         ProfScope ps(ctx, SLOT_CLEAR);
         const uint32_t words = (uint32_t)(ctx->cap / 32 + 1);
         const unsigned nb = (unsigned)std::min<int64_t>(((int64_t)g.ncells / 4 + SC_BLOCK - 1) / SC_BLOCK + 1, 148 * 16);
-        const uint32_t scan_words = (g.ncells + SC_FRONT_TILE - 1) / SC_FRONT_TILE + 1;  // ticket + descriptors
+        const uint32_t scan_words = (g.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;  // ticket + descriptors
         CK(launch_pdl(k_begin_tick, dim3(nb), dim3(SC_BLOCK), ctx->stream, ctx->cnt, ctx->cell_start, g.ncells,
                       ctx->carry_count ? 1 : 0, ctx->wall_bits_cur, ctx->wall_bits_srt, words, ctx->bsum, scan_words,
                       (uint32_t)ctx->cap));
         ctx->carry_count = false;
     }
     ctx->next_clean = false;
-    // The front of the sort: one persistent kernel with grid barriers (k_sort_front), or - with SC_SORT_FUSED=0, and for a
-    // deferred strip unpack - the three separate launches it replaces.
-    const bool fused = sort_fused() && !ctx->pend.on;
-    if (fused) {
-        if (n > 0) {
-            ProfScope ps(ctx, SLOT_SORT_FRONT);
-            const int64_t want = (n + SC_BLOCK * SC_FRONT_ILP - 1) / (SC_BLOCK * SC_FRONT_ILP);
-            const int64_t tiles = ((int64_t)g.ncells + SC_FRONT_TILE - 1) / SC_FRONT_TILE;
-            const unsigned nb = (unsigned)std::max<int64_t>(1, std::min<int64_t>(front_blocks(ctx), std::max(want, tiles)));
-            auto go = [&](bool pdl) {
-                return launch_coop(pdl, k_sort_front<kStep>, dim3(nb), dim3(SC_BLOCK), ctx->stream, ctx->cnt, g, ctx->dp,
-                                   ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot, ctx->cell_start, ctx->wall_bits_cur,
-                                   ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap, ctx->bsum + 1, ctx->tmpidx);
-            };
-            cudaError_t e = go(ctx->front_pdl);
-            if (e != cudaSuccess && ctx->front_pdl) {  // cooperative + programmatic serialization refused: cooperative only
-                fprintf(stderr, "[sandcrate] cooperative + programmatic launch refused (%s): k_sort_front runs cooperative only\n",
-                        cudaGetErrorString(e));
-                cudaGetLastError();
-                ctx->front_pdl = false;
-                e = go(false);
-            }
-            CK(e);
-        } else {
-            CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
-        }
-    } else {
     if (n > 0) {
-            ProfScope ps(ctx, SLOT_PREPASS);
-            CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
-                          ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                          ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
-                          (const uint32_t *)nullptr));
-        }
-        if (ctx->pend.on) {  // strips: now the neighbors' records, then the same pass over just what they appended
-            CKR(flush_pending_unpack(ctx));
-            ProfScope ps(ctx, SLOT_PREPASS);
-            const int64_t m = 2LL * ctx->dist.cap;
-            CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((m + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
-                          ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                          ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
-                          (const uint32_t *)&ctx->cnt->n_split));
-        }
-        CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
-    if (n > 0) {
-        ProfScope ps(ctx, SLOT_PLACE);
-        CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
-                      (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
-                      (const uint32_t *)ctx->cell_start, ctx->tmpidx, (uint32_t)ctx->cap));
+        ProfScope ps(ctx, SLOT_PREPASS);
+        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
+                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
+                      (const uint32_t *)nullptr));
     }
+    if (ctx->pend.on) {  // strips: now the neighbors' records, then the same pass over just what they appended
+        CKR(flush_pending_unpack(ctx));
+        ProfScope ps(ctx, SLOT_PREPASS);
+        const int64_t m = 2LL * ctx->dist.cap;
+        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((m + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
+                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
+                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
+                      (const uint32_t *)&ctx->cnt->n_split));
     }
+    CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
+        {
+            ProfScope ps(ctx, SLOT_PLACE);
+            CK(launch_pdl(k_place, dim3(blocks_for((n + SC_PLACE_ILP - 1) / SC_PLACE_ILP)), dim3(SC_BLOCK), ctx->stream,
+                          (const Counters *)ctx->cnt, (const uint32_t *)ctx->cell_key, (const uint32_t *)ctx->slot,
+                          (const uint32_t *)ctx->cell_start, ctx->tmpidx, (uint32_t)ctx->cap));
+        }
         ProfScope ps(ctx, SLOT_RANK_GATHER);
         if (ctx->precision == SC_PRECISION_F64)
             CK(launch_pdl(k_rank_gather<double>, dim3(blocks_for(n)), dim3(SC_BLOCK), ctx->stream,
@@ -873,7 +809,7 @@ static TickDuty tick_duty(sc_ctx *ctx) {
     const int o = ctx->par ^ 1;
     d.cells = ctx->cell_bufs[o]; d.ncells = ctx->grid.ncells;
     d.bits_a = ctx->wbits_cur[o]; d.bits_b = ctx->wbits_srt[o]; d.nbits = (uint32_t)(ctx->cap / 32 + 1);
-    d.scan_desc = ctx->bsum; d.scan_words = (ctx->grid.ncells + SC_FRONT_TILE - 1) / SC_FRONT_TILE + 1;
+    d.scan_desc = ctx->bsum; d.scan_words = (ctx->grid.ncells + SC_SCAN_TILE - 1) / SC_SCAN_TILE + 1;
     d.cnt = ctx->cnt;
     return d;
 }

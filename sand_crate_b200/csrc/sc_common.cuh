@@ -90,8 +90,6 @@ struct Counters {
     uint32_t pair_cursor;  // next free record of the pair buffer (bump allocator, reset every tick)
     uint32_t n_tmp;        // scratch count (strip decomposition pack / readback)
     uint32_t n_untiled;    // blocks of the tiled K4 that ran in pass-through mode this tick (windows too large to stage)
-    uint32_t barrier;      // arrivals at the grid barriers of k_sort_front; the last block to leave the kernel resets it
-    uint32_t barrier_out;  // blocks that have left k_sort_front
 };
 
 // What the tick's LAST kernel (the force kernel) does for the NEXT tick, spread over its threads, so that a tick does

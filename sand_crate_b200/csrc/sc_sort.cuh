@@ -16,38 +16,6 @@ namespace sc {
 //   kStep = false: cell key only (standalone detect_particle_collisions)
 // particles per thread: the kernel is a chain of two long-latency operations (position load, histogram atomic), so
 // independent chains are interleaved (4 measured the same as 2)
-// calc_virtual_colliders + apply_hard_wall_fix (crate.py:213-243, 202-211) for ONE particle that is not inside the safe
-// rectangle: contacts with the segments whose box it is in; a touching particle stores its pre-fix position in the side
-// list (the force kernel re-derives the contact vectors from it) and is pushed out to exactly one radius.
-__device__ __noinline__ void wall_contacts(Counters *cnt, const DevParams &P, const WallParams &W, uint32_t i, double2 &p,
-                                           double2 *pos, uint32_t *wall_bits, uint32_t *wall_slot, double2 *wall_pre) {
-    int V = 0;
-    double sx = 0, sy = 0;
-    for (int q = 0; q < W.S; ++q) {
-        if (p.x < W.seg_box[q][0] || p.x > W.seg_box[q][1] || p.y < W.seg_box[q][2] || p.y > W.seg_box[q][3])
-            continue;  // cannot be within the touch distance of this segment
-        double cx, cy;
-        const double dist = point_segment(p.x, p.y, W.seg[q][0], W.seg[q][1], W.seg[q][2], W.seg[q][3], cx, cy);
-        if (dist <= P.touch) {
-            const double vcx = (p.x - cx) * 2, vcy = (p.y - cy) * 2;  // crate.py:234
-            double rel = P.r / sqrt(vcx * vcx + vcy * vcy);            // crate.py:206
-            if (rel < 0.5) rel = 0.5;
-            const double ex = vcx * (rel - 0.5), ey = vcy * (rel - 0.5);
-            if (V == 0) { sx = ex; sy = ey; } else { sx += ex; sy += ey; }
-            ++V;
-        }
-    }
-    if (V > 0) {
-        const uint32_t ws = atomicAdd(&cnt->n_wall, 1u);
-        wall_pre[ws] = p;  // contacts are re-derived from this position by the force kernel
-        wall_slot[i] = ws;
-        atomicOr(&wall_bits[i >> 5], 1u << (i & 31));
-        p.x += sx;
-        p.y += sy;
-        pos[i] = p;
-    }
-}
-
 #ifndef SC_PREPASS_ILP
 #define SC_PREPASS_ILP 2
 #endif
@@ -91,7 +59,33 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
             const bool clear = p[u].x > W.safe_contact[0] && p[u].x < W.safe_contact[1] &&
                                p[u].y > W.safe_contact[2] && p[u].y < W.safe_contact[3];
             if (!clear) {
-                wall_contacts(cnt, P, W, i, p[u], pos, wall_bits, wall_slot, wall_pre);
+                int V = 0;
+                double sx = 0, sy = 0;
+                for (int q = 0; q < W.S; ++q) {
+                    if (p[u].x < W.seg_box[q][0] || p[u].x > W.seg_box[q][1] || p[u].y < W.seg_box[q][2] ||
+                        p[u].y > W.seg_box[q][3])
+                        continue;  // cannot be within the touch distance of this segment
+                    double cx, cy;
+                    const double dist = point_segment(p[u].x, p[u].y, W.seg[q][0], W.seg[q][1], W.seg[q][2],
+                                                      W.seg[q][3], cx, cy);
+                    if (dist <= P.touch) {
+                        const double vcx = (p[u].x - cx) * 2, vcy = (p[u].y - cy) * 2;  // crate.py:234
+                        double rel = P.r / sqrt(vcx * vcx + vcy * vcy);                  // crate.py:206
+                        if (rel < 0.5) rel = 0.5;
+                        const double ex = vcx * (rel - 0.5), ey = vcy * (rel - 0.5);
+                        if (V == 0) { sx = ex; sy = ey; } else { sx += ex; sy += ey; }
+                        ++V;
+                    }
+                }
+                if (V > 0) {
+                    const uint32_t ws = atomicAdd(&cnt->n_wall, 1u);
+                    wall_pre[ws] = p[u];  // contacts are re-derived from this position by the force kernel
+                    wall_slot[i] = ws;
+                    atomicOr(&wall_bits[i >> 5], 1u << (i & 31));
+                    p[u].x += sx;
+                    p[u].y += sy;
+                    pos[i] = p[u];
+                }
             }
         }
         int row;
@@ -222,148 +216,6 @@ k_place(const Counters *cnt, const uint32_t *cell_key, const uint32_t *slot,
 #pragma unroll
     for (int u = 0; u < SC_PLACE_ILP; ++u)
         if (c[u] != SC_INVALID_CELL) tmpidx[st[u] + sl[u]] = i0 + u * SC_BLOCK;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// The front of the sort as ONE persistent kernel: wall pre-pass + cell keys + histogram | cell scan | placement, the three
-// phases separated by grid barriers instead of kernel boundaries.  As three launches they were 15.0 + 12.8 + 6.9 us (ncu)
-// for ~6 + 5 + 2 us of memory work: each small kernel pays a grid ramp-up and a tail.  The grid is sized to be co-resident
-// (blocks per SM from the occupancy API x SMs), which is what makes a spinning barrier safe; the dependent launch is
-// released only after the last barrier, so the next kernel's blocks cannot take slots this grid still needs.
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (ld_acquire_gpu(counter) < target) {}
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-#define SC_FRONT_ILP 4                                  // particles per thread and pass in the pre-pass phase
-#define SC_FRONT_TILE (SC_BLOCK * SC_SCAN_ITEMS)        // cells per scan tile of the fused kernel (4096)
-template <bool kStep>
-__global__ void __launch_bounds__(SC_BLOCK, 4)
-k_sort_front(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
-             double2 *pos, uint32_t *cell_key, uint32_t *slot,
-             uint32_t *cells, uint32_t *wall_bits, uint32_t *wall_slot,
-             double2 *wall_pre, uint32_t cap, unsigned long long *desc, uint32_t *tmpidx) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const uint32_t n = cnt->n < cap ? cnt->n : cap;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (cnt->n > cap) cnt->overflow = 1u;
-        cnt->pair_cursor = 0; cnt->n_untiled = 0;  // consumed by this tick's density kernel
-    }
-    // ---- phase A: remove_particles, wall contacts + hard wall fix, cell keys, histogram with arrival slots -------------
-    for (uint32_t base = blockIdx.x * (SC_BLOCK * SC_FRONT_ILP); base < n; base += gridDim.x * (SC_BLOCK * SC_FRONT_ILP)) {
-        const uint32_t i0 = base + threadIdx.x;
-        double2 p[SC_FRONT_ILP];
-        uint32_t c[SC_FRONT_ILP];
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u) {
-            const uint32_t i = i0 + u * SC_BLOCK;
-            if (i < n) p[u] = pos[i];
-        }
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u) {
-            const uint32_t i = i0 + u * SC_BLOCK;
-            c[u] = SC_INVALID_CELL;
-            if (i >= n) continue;
-            if (kStep) {
-                const bool out = (p[u].x < P.box_lo) | (p[u].x > P.box_hi) | (p[u].y < P.box_lo) | (p[u].y > P.box_hi);
-                if (out) { cell_key[i] = SC_INVALID_CELL; continue; }
-                if (!(p[u].x > W.safe_contact[0] && p[u].x < W.safe_contact[1] && p[u].y > W.safe_contact[2] &&
-                      p[u].y < W.safe_contact[3]))
-                    wall_contacts(cnt, P, W, i, p[u], pos, wall_bits, wall_slot, wall_pre);
-            }
-            int row;
-            c[u] = cell_of(g, p[u].x, p[u].y, row);
-        }
-        uint32_t sl[SC_FRONT_ILP];
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u)
-            if (c[u] != SC_INVALID_CELL) sl[u] = atomicAdd(&cells[c[u]], 1u);
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u) {
-            const uint32_t i = i0 + u * SC_BLOCK;
-            if (c[u] != SC_INVALID_CELL) { cell_key[i] = c[u]; slot[i] = sl[u]; }
-        }
-    }
-    grid_barrier(&cnt->barrier, gridDim.x);
-    // ---- phase B: exclusive scan of the cell counts, in place; total to cells[ncells].  Tiles in increasing order per
-    // block, every block resident: a tile only ever waits for lower tiles, which are done or being worked on -----------
-    {
-        __shared__ uint32_t s_prefix;
-        const uint32_t ncells = g.ncells;
-        const uint32_t ntiles = (ncells + SC_FRONT_TILE - 1u) / SC_FRONT_TILE;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const uint32_t base = tile * SC_FRONT_TILE + threadIdx.x * SC_SCAN_ITEMS;
-            uint32_t item[SC_SCAN_ITEMS];
-            scan_load(cells, ncells, base, item);
-            uint32_t v = 0;
-#pragma unroll
-            for (int q = 0; q < SC_SCAN_ITEMS; ++q) v += item[q];
-            uint32_t total;
-            const uint32_t before = block_exclusive_scan_n<SC_BLOCK>(v, total);
-            if (threadIdx.x == 0) st_desc(desc + tile, (1ull << 32) | total);
-            uint32_t part = 0;
-            for (uint32_t t = threadIdx.x; t < tile; t += SC_BLOCK) {
-                unsigned long long d;
-                do { d = ld_desc(desc + t); } while ((d >> 32) == 0ull);
-                part += (uint32_t)d;
-            }
-            uint32_t prefix;
-            block_exclusive_scan_n<SC_BLOCK>(part, prefix);
-            if (threadIdx.x == 0) s_prefix = prefix;
-            __syncthreads();
-            uint32_t run = s_prefix + before;
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < SC_SCAN_ITEMS; ++q) {
-                const uint32_t t = item[q];
-                item[q] = run;
-                run += t;
-            }
-            if (base + SC_SCAN_ITEMS <= ncells) {
-                uint4 *o = reinterpret_cast<uint4 *>(cells + base);
-#pragma unroll
-                for (int q = 0; q < SC_SCAN_ITEMS / 4; ++q) o[q] = make_uint4(item[4 * q], item[4 * q + 1], item[4 * q + 2], item[4 * q + 3]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < SC_SCAN_ITEMS; ++q)
-                    if (base + q < ncells) cells[base + q] = item[q];
-            }
-            if (tile == ntiles - 1u && threadIdx.x == SC_BLOCK - 1) cells[ncells] = run;  // grand total = live count
-        }
-        if (ntiles == 0u && blockIdx.x == 0 && threadIdx.x == 0) cells[ncells] = 0u;
-    }
-    grid_barrier(&cnt->barrier, 2u * gridDim.x);
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    // ---- phase C: counting-sort placement (arrival order inside a cell; k_rank_gather makes it deterministic) ----------
-    for (uint32_t base = blockIdx.x * (SC_BLOCK * SC_FRONT_ILP); base < n; base += gridDim.x * (SC_BLOCK * SC_FRONT_ILP)) {
-        const uint32_t i0 = base + threadIdx.x;
-        uint32_t c[SC_FRONT_ILP], sl[SC_FRONT_ILP], st[SC_FRONT_ILP];
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u) {
-            const uint32_t i = i0 + u * SC_BLOCK;
-            c[u] = SC_INVALID_CELL;
-            if (i < n) { c[u] = cell_key[i]; sl[u] = slot[i]; }
-        }
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u)
-            if (c[u] != SC_INVALID_CELL) st[u] = cells[c[u]];
-#pragma unroll
-        for (int u = 0; u < SC_FRONT_ILP; ++u)
-            if (c[u] != SC_INVALID_CELL) tmpidx[st[u] + sl[u]] = i0 + u * SC_BLOCK;
-    }
-    // the barrier counter re-arms itself: the last block to leave zeroes it (nobody is spinning on it any more)
-    if (threadIdx.x == 0 && atomicAdd(&cnt->barrier_out, 1u) == gridDim.x - 1u) { cnt->barrier = 0u; cnt->barrier_out = 0u; }
 }
 
 // K3: rank inside the cell by (x, uid) and gather the particle record to its final sorted position.
