@@ -231,7 +231,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count()},
     }
-    if not a.no_numpy_reference:
+    if not a.no_numpy_reference and world_size == 1:   # once per round is enough: it does not depend on N
         line["numpy_reference"] = numpy_reference_block(scene)
     emit(line)
 
