@@ -139,31 +139,41 @@ def _ptr(a, typ):
     return a.ctypes.data_as(typ) if a is not None else None
 
 
-class PinnedArray:
-    """A NumPy array over page-locked host memory (sc_host_alloc); freed when this object is closed or collected."""
+class _PinnedBlock:
+    """One cudaHostAlloc allocation; freed when the last reference to it goes."""
 
-    def __init__(self, shape, dtype=np.float64):
-        self._L = load()
-        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
-        self.dtype = np.dtype(dtype)
-        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+    def __init__(self, L, nbytes):
+        self._L = L
         self._p = C.c_void_p()
-        if self._L.sc_host_alloc(max(nbytes, 1), C.byref(self._p)):
-            raise SandCrateError(self._L.sc_last_error(None).decode())
-        raw = (C.c_byte * max(nbytes, 1)).from_address(self._p.value)
-        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
-
-    def close(self):
-        if getattr(self, "_p", None) is not None and self._p.value:
-            self.array = None
-            self._L.sc_host_free(self._p)
-            self._p = C.c_void_p()
+        if L.sc_host_alloc(max(nbytes, 1), C.byref(self._p)):
+            raise SandCrateError(L.sc_last_error(None).decode())
 
     def __del__(self):
         try:
-            self.close()
+            if self._p.value:
+                self._L.sc_host_free(self._p)
+                self._p = C.c_void_p()
         except Exception:
             pass
+
+
+class PinnedArray:
+    """A NumPy array over page-locked host memory (sc_host_alloc).  The memory belongs to the ARRAY: every view of it
+    keeps the allocation alive (NumPy base chain -> ctypes buffer -> block), so an array handed out by `Crate.particles`
+    stays valid for as long as somebody holds it - like the reference's own arrays - even after the context that filled
+    it is closed or has grown a larger buffer.  `close()` only drops this object's reference."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        block = _PinnedBlock(load(), nbytes)
+        raw = (C.c_byte * max(nbytes, 1)).from_address(block._p.value)
+        raw._block = block   # the ctypes buffer (which NumPy keeps as the array's base) owns the allocation
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def close(self):
+        self.array = None
 
 
 class Context:
@@ -193,8 +203,6 @@ class Context:
         bufs = self.__dict__.setdefault("_pinned", {})
         b = bufs.get(name)
         if b is None or b.shape[0] < rows:
-            if b is not None:
-                b.close()
             b = bufs[name] = PinnedArray((max(rows, self.capacity),) + tuple(shape_tail), dtype)
         return b.array
 

@@ -420,7 +420,13 @@ def test_crate_readback_is_page_locked_and_refilled_in_place():
     assert np.shares_memory(p1[:1], p2[:1]) or len(p2) != len(p1)   # same buffer again
     assert not np.array_equal(p2[:len(keep)], keep[:len(p2)])        # and it now holds the new tick
     assert len(crate.particle_velocities) == len(p2) == len(crate.particles_pressure)
+    # the page-locked memory belongs to the arrays, not to the context: what was handed out stays readable after close()
+    # (it used to be freed under the caller's feet)
+    last = p2.copy()
     crate.close()
+    import gc
+    gc.collect()
+    assert np.array_equal(p2, last) and np.array_equal(p1[:len(last)], last[:len(p1)])
 
 
 def test_mixed_mode_drift_stays_bounded_over_1000_ticks():
