@@ -92,10 +92,11 @@ struct sc_ctx {
     WireHeader *wire_dummy = nullptr;  // stands in for a missing neighbor's buffers (+ push completion counters)
     WireHeader *send_lo = nullptr, *send_hi = nullptr;  // the send buffers of the last sc_dist_pack (re-armed by unpack)
     unsigned push_toggle = 0;
-    // The unpack kernel waits for the neighbors' records, and nothing of the tick's first pass over the particles this
-    // rank already holds (walls, cell keys) depends on them: the unpack is therefore DEFERRED - recorded here by
-    // sc_dist_unpack[_flagged] and launched by the step after that pass, followed by a second, small pass over what it
-    // appended.  The neighbors' latency hides behind ~20 us of work instead of standing at the head of the tick.
+    // The unpack waits for the neighbors' records, and nothing of the tick's first pass over the particles this rank
+    // already holds (walls, cell keys) depends on them: the unpack is therefore DEFERRED - recorded here by
+    // sc_dist_unpack[_flagged] and carried out by the step's pre-pass itself (PrepassUnpack), whose blocks behind the
+    // particles already held wait for the flags and read the receive buffers directly.  One launch less on the critical
+    // path; the neighbors' latency hides behind the pass over the resident particles.
     struct { bool on = false; const void *recv_lo = nullptr, *flag_lo = nullptr, *recv_hi = nullptr, *flag_hi = nullptr;
              uint32_t value = 0; } pend;
     int64_t launches = 0;
@@ -719,21 +720,27 @@ template <bool kStep> static int enqueue_search(sc_ctx *ctx) {
         ctx->carry_count = false;
     }
     ctx->next_clean = false;
+    // strips: a recorded (deferred) unpack is carried out by the pre-pass itself (PrepassUnpack, sc_common.cuh)
+    PrepassUnpack U{};
+    if (ctx->pend.on) {
+        U.on = 1; U.vel_is_f64 = ctx->precision == SC_PRECISION_F64;
+        U.lo = UnpackSide{ctx->dist.has_lo ? (const WireHeader *)ctx->pend.recv_lo : nullptr, (const uint32_t *)ctx->pend.flag_lo};
+        U.hi = UnpackSide{ctx->dist.has_hi ? (const WireHeader *)ctx->pend.recv_hi : nullptr, (const uint32_t *)ctx->pend.flag_hi};
+        U.value = ctx->pend.value; U.wire_cap = ctx->dist.cap;
+        U.vel = ctx->vel_cur; U.uid = ctx->uid_cur;
+        U.send_lo = ctx->send_lo ? ctx->send_lo : ctx->wire_dummy;
+        U.send_hi = ctx->send_hi ? ctx->send_hi : ctx->wire_dummy + 1;
+        if (!U.lo.hdr && !U.hi.hdr) U.on = 0;
+        ctx->pend.on = false;
+    }
     if (n > 0) {
         ProfScope ps(ctx, SLOT_PREPASS);
-        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
-                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
-                      (const uint32_t *)nullptr));
-    }
-    if (ctx->pend.on) {  // strips: now the neighbors' records, then the same pass over just what they appended
-        CKR(flush_pending_unpack(ctx));
-        ProfScope ps(ctx, SLOT_PREPASS);
-        const int64_t m = 2LL * ctx->dist.cap;
-        CK(launch_pdl(k_prepass<kStep>, dim3(blocks_for((m + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
-                      ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
-                      ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap,
-                      (const uint32_t *)&ctx->cnt->n_split));
+        auto go = [&](auto kernel) {
+            return launch_pdl(kernel, dim3(blocks_for((n + SC_PREPASS_ILP - 1) / SC_PREPASS_ILP)), dim3(SC_BLOCK),
+                              ctx->stream, ctx->cnt, g, ctx->dp, ctx->walls, ctx->pos_cur, ctx->cell_key, ctx->slot,
+                              ctx->cell_start, ctx->wall_bits_cur, ctx->wall_slot_cur, ctx->wall_pre, (uint32_t)ctx->cap, U);
+        };
+        CK(U.on ? go(k_prepass<kStep, true>) : go(k_prepass<kStep, false>));
     }
     CKR(exclusive_scan(ctx, ctx->cell_start, g.ncells, SLOT_SCAN, true));
     if (n > 0) {
@@ -1514,10 +1521,9 @@ static int flush_pending_unpack(sc_ctx *ctx) {
 }
 
 static bool defer_unpack() {
-    // SC_DIST_DEFER=1 (developer switch): measured on 2xB200 the deferral costs more than it hides - 264.6 vs 260.1 us
-    // per tick (the ranks run in lockstep, so the flag has arrived anyway and the extra launch is pure cost)
+    // SC_DIST_DEFER=0 (developer switch): launch k_dist_unpack where sc_dist_unpack is called (A/B timing)
     static int v = -1;
-    if (v < 0) { const char *e = getenv("SC_DIST_DEFER"); v = e ? atoi(e) : 0; }
+    if (v < 0) { const char *e = getenv("SC_DIST_DEFER"); v = e ? atoi(e) : 1; }
     return v != 0;
 }
 

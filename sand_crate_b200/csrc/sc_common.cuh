@@ -79,6 +79,40 @@ struct WallParams {
     float safe_ccd_f32[4];  // safe_ccd shrunk by 1e-6: the mixed-precision kernel tests the movement in fp32 first
 };
 
+// ---- strip decomposition: what the wire looks like (kernels in sc_dist.cuh; the pre-pass reads it too) ----------------
+#define SC_GHOST_BIT 0x80000000u
+#define SC_WIRE_MIGRANT 0u
+#define SC_WIRE_HALO 1u
+
+// 16-byte header followed by `count` records
+struct WireHeader { uint32_t count, overflow, too_far, pad_; };
+struct __align__(8) WireRec { double px, py, vx, vy; uint32_t uid, kind; };  // 40 bytes
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == NULL: the data is already there
+// The strip unpack done by the PRE-PASS itself (sc_sort.cuh k_prepass): the blocks that cover the indices behind the
+// particles this rank already holds wait for the neighbors' flags, read their records straight from the receive buffers,
+// append them and go on with walls and cell keys for them - one launch less on the tick's critical path, and the wait for
+// the neighbors hides behind the pass over the particles that were already here.
+struct PrepassUnpack {
+    int on;                 // 0: ordinary pass
+    int vel_is_f64;
+    UnpackSide lo, hi;
+    uint32_t value, wire_cap;
+    void *vel;              // float2* / double2*
+    uint32_t *uid;
+    WireHeader *send_lo, *send_hi;  // re-armed for the next pack
+};
+
+
 // device-resident counters, zeroed/updated on the stream (no host round trip in the step)
 struct Counters {
     uint32_t n;          // live particles at the start of the tick (= after the previous tick's removal)

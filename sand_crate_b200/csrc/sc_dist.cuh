@@ -17,14 +17,6 @@
 
 namespace sc {
 
-#define SC_GHOST_BIT 0x80000000u
-#define SC_WIRE_MIGRANT 0u
-#define SC_WIRE_HALO 1u
-
-// 16-byte header followed by `count` records
-struct WireHeader { uint32_t count, overflow, too_far, pad_; };
-struct __align__(8) WireRec { double px, py, vx, vy; uint32_t uid, kind; };  // 40 bytes
-
 struct DistCfg {
     long long row_lo, row_hi;  // owned rows: row_lo <= floor(y / d) < row_hi
     long long far_lo, far_hi;  // rows owned by the two neighbors: far_lo <= row < row_lo below, row_hi <= row < far_hi
@@ -84,15 +76,6 @@ struct PackOut {
     WireRec *recs;     // where the records go: the local send buffer, or the neighbor's receive buffer (kDirect)
     WireHeader *peer_hdr; uint32_t *peer_flag;  // kDirect only
 };
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 template <typename Real, bool kDirect>
 __global__ void __launch_bounds__(SC_BLOCK)
@@ -171,8 +154,6 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
         }
     }
 }
-
-struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == NULL: the data is already there
 
 // both neighbors' buffers in one launch (blockIdx.y = side).  With the direct NVLink transport every block first
 // waits for BOTH flags to reach `value` (raised by the neighbors' pack kernels, which run on other GPUs).  Where a record

@@ -19,15 +19,15 @@ namespace sc {
 #ifndef SC_PREPASS_ILP
 #define SC_PREPASS_ILP 2
 #endif
-template <bool kStep>
+template <bool kStep, bool kUnpack = false>  // kUnpack: the strip variant that appends the neighbors' records itself
 __global__ void __launch_bounds__(SC_BLOCK, 6)  // the wall path may spill; it is rare
 k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams W,
           double2 *pos, uint32_t *cell_key, uint32_t *slot,
           uint32_t *cell_count, uint32_t *wall_bits, uint32_t *wall_slot,
-          double2 *wall_pre, uint32_t cap, const uint32_t *first_ptr) {
+          double2 *wall_pre, uint32_t cap, PrepassUnpack U) {
     pdl_enter();
-    // first_ptr: the pass covers [*first_ptr, n) - the particles the strip exchange appended after the main pass ran
-    const uint32_t i0 = (first_ptr ? *first_ptr : 0u) + blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP) + threadIdx.x;
+    const uint32_t b0 = blockIdx.x * (SC_BLOCK * SC_PREPASS_ILP);
+    const uint32_t i0 = b0 + threadIdx.x;
     // the positions are requested BEFORE the live count is known (any index below the capacity is readable): the count
     // is itself a device-resident value, and waiting for it first put one more memory latency at the head of every thread
     double2 p[SC_PREPASS_ILP];
@@ -37,12 +37,51 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
         const uint32_t i = i0 + u * SC_BLOCK;
         if (i < cap) p[u] = pos[i];
     }
-    // the strip exchange appends with an atomic counter and only flags an overflow: every kernel bounds its indices by
-    // the count, so the count itself must never exceed the arrays
-    const uint32_t n = cnt->n < cap ? cnt->n : cap;
+    // every kernel bounds its indices by the count, so the count itself must never exceed the arrays
+    uint32_t n = cnt->n < cap ? cnt->n : cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (cnt->n > cap) cnt->overflow = 1u;
         cnt->pair_cursor = 0; cnt->n_untiled = 0;  // consumed by this tick's density kernel
+    }
+    // strips: the neighbors' records are appended HERE (PrepassUnpack).  n_own = the particles already held; a record's
+    // place is a pure function of its position in its buffer (lower neighbor's first), so the order is deterministic.
+    uint32_t n_own = n, c_lo = 0u;
+    if constexpr (kUnpack) {
+        __shared__ uint32_t s_cnt[2];
+        n_own = cnt->n_split < cap ? cnt->n_split : cap;
+        n = n_own;
+        if (b0 >= n_own + 2u * U.wire_cap) return;  // behind anything the neighbors can send
+        if (b0 + SC_BLOCK * SC_PREPASS_ILP > n_own) {  // this block reaches into the appended range: it needs the records
+            if (threadIdx.x == 0) {
+                if (U.lo.hdr && U.lo.flag) while ((int)(ld_acquire_sys(U.lo.flag) - U.value) < 0) __nanosleep(64);
+                if (U.hi.hdr && U.hi.flag) while ((int)(ld_acquire_sys(U.hi.flag) - U.value) < 0) __nanosleep(64);
+                const uint32_t a = U.lo.hdr ? (U.lo.hdr->count < U.wire_cap ? U.lo.hdr->count : U.wire_cap) : 0u;
+                const uint32_t b = U.hi.hdr ? (U.hi.hdr->count < U.wire_cap ? U.hi.hdr->count : U.wire_cap) : 0u;
+                s_cnt[0] = a; s_cnt[1] = b;
+                if (b0 <= n_own) {  // the one block that holds index n_own publishes the new count, re-arms the send buffers
+                    cnt->n = n_own + a + b;   // (the next kernels clamp it and raise the flag)
+                    if (n_own + a + b > cap) cnt->overflow = 1u;
+                    U.send_lo->count = 0u; U.send_hi->count = 0u;
+                }
+            }
+            __syncthreads();
+            c_lo = s_cnt[0];
+            const uint32_t total = n_own + c_lo + s_cnt[1];
+            n = total < cap ? total : cap;
+#pragma unroll
+            for (int u = 0; u < SC_PREPASS_ILP; ++u) {
+                const uint32_t i = i0 + u * SC_BLOCK;
+                if (i < n_own || i >= n) continue;
+                const uint32_t k = i - n_own;
+                const WireRec r = k < c_lo ? reinterpret_cast<const WireRec *>(U.lo.hdr + 1)[k]
+                                           : reinterpret_cast<const WireRec *>(U.hi.hdr + 1)[k - c_lo];
+                p[u] = make_double2(r.px, r.py);
+                pos[i] = p[u];
+                if (U.vel_is_f64) reinterpret_cast<double2 *>(U.vel)[i] = make_double2(r.vx, r.vy);
+                else reinterpret_cast<float2 *>(U.vel)[i] = make_float2((float)r.vx, (float)r.vy);
+                U.uid[i] = r.kind == SC_WIRE_HALO ? (r.uid | SC_GHOST_BIT) : r.uid;
+            }
+        }
     }
 #pragma unroll
     for (int u = 0; u < SC_PREPASS_ILP; ++u) {
