@@ -193,24 +193,22 @@ int64_t sc_debug_untiled_blocks(sc_ctx *ctx);
  * (sand_crate_b200/strips.py) additionally requires closed scenes (no particle sources) and fixed walls; on a context
  * with a neighbor, sc_get_state / sc_get_uids / the parity taps return an error - read back with sc_dist_get_owned. */
 int64_t sc_dist_wire_bytes(int64_t wire_capacity);
-int64_t sc_dist_peer_bytes(int64_t wire_capacity); /* size of a receive slot of the direct transport (tagged words) */
 int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t row_hi, int halo_rows,
                       int64_t wire_capacity);
 int sc_dist_pack(sc_ctx *ctx, void *send_lo_dev, void *send_hi_dev);
 int sc_dist_unpack(sc_ctx *ctx, const void *recv_lo_dev, const void *recv_hi_dev);
-/* Direct NVLink transport instead of send/recv: sc_dist_pack_push (below) writes the records into the neighbors' receive
- * buffers through peer-mapped device pointers (e.g. torch symmetric memory); sc_dist_unpack_flagged is sc_dist_unpack for
- * buffers filled that way: `value` is the tag the records were sent with (use the tick number + 1: never 0, never
- * repeated; double-buffer the receive slots by tick parity), the kernel waits on the device until the records carrying it
- * have arrived.  NULL where there is no neighbor. */
+/* Direct NVLink transport instead of send/recv.  sc_dist_push copies header + used records of both packed buffers
+ * into the neighbors' receive buffers through peer-mapped device pointers (e.g. torch symmetric memory) and then
+ * stores `value` (release, system scope) to each neighbor's flag word; sc_dist_unpack_flagged is sc_dist_unpack whose
+ * kernel first waits (on the device) until this rank's flag words have reached `value`.  Use the tick number as
+ * `value`: monotonic, never reset.  NULL where there is no neighbor. */
+int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev,
+                 const void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value);
 int sc_dist_unpack_flagged(sc_ctx *ctx, const void *recv_lo_dev, const void *flag_lo_dev, const void *recv_hi_dev,
                            const void *flag_hi_dev, uint32_t value);
-/* Pack and transfer as ONE kernel: the records are written straight into the neighbors' receive buffers
- * (sc_dist_peer_bytes each) as they are produced - peer stores over NVLink, every 8-byte store carrying 4 bytes of payload
- * and `value` as a tag, so that a record validates itself and no fence or flag is needed; the last block to finish
- * publishes the tagged record counts.  The receiving side is sc_dist_unpack_flagged with the same `value` (its flag
- * pointers only select this format; the flag words are not used).  send_*_dev are still needed: their headers hold the
- * record counters and the sticky overflow / too_far marks. */
+/* sc_dist_pack and sc_dist_push as ONE kernel: the records are written straight into the neighbors' receive buffers
+ * as they are produced (peer stores over NVLink), the last block to finish publishes the counts and raises the flags.
+ * send_*_dev are still needed (their headers hold the record counters and the sticky overflow / too_far marks). */
 int sc_dist_pack_push(sc_ctx *ctx, void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev, void *send_hi_dev,
                       void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value);
 /* owned particles of this rank, in arbitrary order; uid[i] identifies row i.  Synchronises. */

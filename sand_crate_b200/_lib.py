@@ -79,10 +79,10 @@ SIGNATURES = {
     "sc_points_to_segments_distance": (C.c_int, [_ctx, _dp, C.c_int64, _dp, C.c_int, _dp, _dp]),
     "sc_pad_segments": (C.c_int, [_dp, C.c_int, C.c_double, _dp]),
     "sc_dist_wire_bytes": (C.c_int64, [C.c_int64]),
-    "sc_dist_peer_bytes": (C.c_int64, [C.c_int64]),
     "sc_dist_configure": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int64]),
     "sc_dist_pack": (C.c_int, [_ctx, C.c_void_p, C.c_void_p]),
     "sc_dist_unpack": (C.c_int, [_ctx, C.c_void_p, C.c_void_p]),
+    "sc_dist_push": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_unpack_flagged": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_pack_push": (C.c_int, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "sc_dist_get_owned": (C.c_int, [_ctx, _dp, _dp, _up, C.c_int64, _lp]),
@@ -367,6 +367,12 @@ class Context:
     def dist_unpack(self, recv_lo, recv_hi):
         self._ck(self._L.sc_dist_unpack(self._h, self._devptr(recv_lo), self._devptr(recv_hi)))
 
+    def dist_push(self, lo, hi, value):
+        """lo / hi: None or (send buffer, peer receive address, peer flag address)."""
+        lo, hi = lo or (None, None, None), hi or (None, None, None)
+        self._ck(self._L.sc_dist_push(self._h, *[self._devptr(x) for x in lo], *[self._devptr(x) for x in hi],
+                                      C.c_uint32(value)))
+
     def dist_pack_push(self, lo, hi, value):
         """pack + push fused.  lo / hi: None or (send buffer, peer receive address, peer flag address)."""
         lo, hi = lo or (None, None, None), hi or (None, None, None)
@@ -465,10 +471,6 @@ def source_uniform(seed: int, tick: int, source_index: int, j: int) -> float:
 
 def wire_bytes(wire_capacity: int) -> int:
     return int(load().sc_dist_wire_bytes(int(wire_capacity)))
-
-
-def peer_bytes(wire_capacity: int) -> int:
-    return int(load().sc_dist_peer_bytes(int(wire_capacity)))
 
 
 def pad_segments(segments, pad):

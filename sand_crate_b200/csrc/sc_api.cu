@@ -1330,10 +1330,6 @@ static int dist_ready(sc_ctx *ctx, const char *who) {
 extern "C" int64_t sc_dist_wire_bytes(int64_t wire_capacity) {
     return (int64_t)sizeof(WireHeader) + (int64_t)sizeof(WireRec) * wire_capacity;
 }
-// a receive slot of the direct transport: every 4 payload bytes travel with a 4-byte tag (LL records, sc_common.cuh)
-extern "C" int64_t sc_dist_peer_bytes(int64_t wire_capacity) {
-    return (int64_t)sizeof(WireHeader) + (int64_t)sizeof(WireWord) * SC_WIRE_LL_WORDS * wire_capacity;
-}
 
 extern "C" int sc_dist_configure(sc_ctx *ctx, int rank, int nranks, int64_t row_lo, int64_t row_hi, int halo_rows,
                                  int64_t wire_capacity) {
@@ -1464,8 +1460,8 @@ static int enqueue_pack(sc_ctx *ctx, const char *who, void *send_lo_dev, void *s
     }
     PackOut plo{lo, reinterpret_cast<WireRec *>(lo + 1), nullptr, nullptr}, phi{hi, reinterpret_cast<WireRec *>(hi + 1), nullptr, nullptr};
     if (direct) {
-        if (ctx->dist.has_lo) { plo.peer_hdr = (WireHeader *)peer_recv_lo; plo.peer_flag = (uint32_t *)peer_flag_lo; }
-        if (ctx->dist.has_hi) { phi.peer_hdr = (WireHeader *)peer_recv_hi; phi.peer_flag = (uint32_t *)peer_flag_hi; }
+        if (ctx->dist.has_lo) { plo.peer_hdr = (WireHeader *)peer_recv_lo; plo.recs = reinterpret_cast<WireRec *>(plo.peer_hdr + 1); plo.peer_flag = (uint32_t *)peer_flag_lo; }
+        if (ctx->dist.has_hi) { phi.peer_hdr = (WireHeader *)peer_recv_hi; phi.recs = reinterpret_cast<WireRec *>(phi.peer_hdr + 1); phi.peer_flag = (uint32_t *)peer_flag_hi; }
     }
     uint32_t *done = reinterpret_cast<uint32_t *>(ctx->wire_dummy + 3);  // "blocks done" counter of the fused kernel
     if (launch_n > 0) {
@@ -1556,6 +1552,28 @@ extern "C" int sc_dist_unpack_flagged(sc_ctx *ctx, const void *recv_lo_dev, cons
                                       const void *recv_hi_dev, const void *flag_hi_dev, uint32_t value) {
     CKR(dist_ready(ctx, "sc_dist_unpack_flagged"));
     return enqueue_unpack(ctx, recv_lo_dev, flag_lo_dev, recv_hi_dev, flag_hi_dev, value);
+}
+
+extern "C" int sc_dist_push(sc_ctx *ctx, const void *send_lo_dev, void *peer_recv_lo_dev, void *peer_flag_lo_dev,
+                            const void *send_hi_dev, void *peer_recv_hi_dev, void *peer_flag_hi_dev, uint32_t value) {
+    CKR(dist_ready(ctx, "sc_dist_push"));
+    uint32_t *done = reinterpret_cast<uint32_t *>(ctx->wire_dummy + 2);  // "blocks done" counters, one per direction
+    PushSide lo{nullptr, nullptr, nullptr, done}, hi{nullptr, nullptr, nullptr, done + 1};
+    if (ctx->dist.has_lo) {
+        if (!send_lo_dev || !peer_recv_lo_dev || !peer_flag_lo_dev) return fail(ctx, "sc_dist_push: NULL lower buffer");
+        lo.src = (const WireHeader *)send_lo_dev; lo.peer_dst = peer_recv_lo_dev; lo.peer_flag = (uint32_t *)peer_flag_lo_dev;
+    }
+    if (ctx->dist.has_hi) {
+        if (!send_hi_dev || !peer_recv_hi_dev || !peer_flag_hi_dev) return fail(ctx, "sc_dist_push: NULL upper buffer");
+        hi.src = (const WireHeader *)send_hi_dev; hi.peer_dst = peer_recv_hi_dev; hi.peer_flag = (uint32_t *)peer_flag_hi_dev;
+    }
+    if (!lo.src && !hi.src) return 0;
+    ProfScope ps(ctx, SLOT_DIST_PUSH);
+    const size_t bytes = sizeof(WireHeader) + (size_t)ctx->dist.cap * sizeof(WireRec);
+    const unsigned nb = (unsigned)std::min<size_t>((bytes / 16 + SC_BLOCK - 1) / SC_BLOCK, 64);
+    CK(launch_maybe_pdl(dist_pdl_mask() & 2, k_wire_push, dim3(nb, 2), dim3(SC_BLOCK), ctx->stream, lo, hi, ctx->dist.cap, value));
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // NOTE: unpack's kernels clamp the appended count on overflow only by flagging; cnt->n may exceed cap by the number

@@ -97,62 +97,7 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
     return v;
 }
 
-// Direct (NVLink) transport: SELF-VALIDATING records, no memory fence anywhere.  Every 8-byte store carries 4 bytes of
-// payload and the tick's tag (8-byte stores are single-copy atomic), a record is its ten words, the header is one
-// {count, tag} word written by the last block of the sender's pack kernel.  The receiver polls the header, then each
-// record's words, until the tags match: whatever has arrived is used as soon as it has arrived, in whatever order the
-// stores land.  (The first version fenced every block to system scope and raised a flag: MEMBAR.SYS alone was ~10 us
-// of the pack kernel's 23.)  Tags are the tick number + 1 (never 0, never repeated; slots are double buffered).
-struct __align__(8) WireWord { uint32_t data, tag; };
-#define SC_WIRE_LL_WORDS 10  // sizeof(WireRec) / 4
-__device__ __forceinline__ WireWord ld_wire_word(const WireWord *p) {
-    WireWord w;
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.data), "=r"(w.tag) : "l"(p) : "memory");
-    return w;
-}
-__device__ __forceinline__ void st_wire_word(WireWord *p, uint32_t data, uint32_t tag) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
-}
-// record k of an LL buffer (header word first, 16 bytes reserved for it)
-__device__ __forceinline__ WireWord *ll_record(void *buf, uint32_t k) {
-    return reinterpret_cast<WireWord *>(reinterpret_cast<char *>(buf) + 16) + (size_t)k * SC_WIRE_LL_WORDS;
-}
-__device__ __forceinline__ void ll_store(void *buf, uint32_t k, const WireRec &r, uint32_t tag) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(&r);
-    WireWord *dst = ll_record(buf, k);
-#pragma unroll
-    for (int j = 0; j < SC_WIRE_LL_WORDS; ++j) st_wire_word(dst + j, w[j], tag);
-}
-__device__ __forceinline__ WireRec ll_load(const void *buf, uint32_t k, uint32_t tag) {
-    WireRec r;
-    uint32_t *w = reinterpret_cast<uint32_t *>(&r);
-    const WireWord *src = ll_record(const_cast<void *>(buf), k);
-#pragma unroll
-    for (int j = 0; j < SC_WIRE_LL_WORDS; ++j) {
-        WireWord v;
-        do { v = ld_wire_word(src + j); } while (v.tag != tag);
-        w[j] = v.data;
-    }
-    return r;
-}
-__device__ __forceinline__ uint32_t ll_wait_count(const void *buf, uint32_t tag, uint32_t wire_cap) {
-    WireWord h;
-    do { h = ld_wire_word(reinterpret_cast<const WireWord *>(buf)); } while (h.tag != tag);
-    return h.data < wire_cap ? h.data : wire_cap;
-}
-
-// a receive buffer: `flag` != NULL marks the direct transport (LL records, validated by tag; the flag word itself is no
-// longer used); NULL = plain 40-byte records that are already there (NCCL transport)
-struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };
-__device__ __forceinline__ uint32_t unpack_count(const UnpackSide &s, uint32_t value, uint32_t wire_cap) {
-    if (!s.hdr) return 0u;
-    if (s.flag) return ll_wait_count(s.hdr, value, wire_cap);
-    return s.hdr->count < wire_cap ? s.hdr->count : wire_cap;
-}
-__device__ __forceinline__ WireRec unpack_record(const UnpackSide &s, uint32_t k, uint32_t value) {
-    if (s.flag) return ll_load(s.hdr, k, value);
-    return reinterpret_cast<const WireRec *>(s.hdr + 1)[k];
-}
+struct UnpackSide { const WireHeader *hdr; const uint32_t *flag; };  // flag == NULL: the data is already there
 // The strip unpack done by the PRE-PASS itself (sc_sort.cuh k_prepass): the blocks that cover the indices behind the
 // particles this rank already holds wait for the neighbors' flags, read their records straight from the receive buffers,
 // append them and go on with walls and cell keys for them - one launch less on the tick's critical path, and the wait for

@@ -28,16 +28,6 @@ struct DistCfg {
     uint32_t cap;              // records per wire buffer
 };
 
-struct PackRange {
-    const uint32_t *cell_start;  // last tick's cell boundaries, or NULL: cover all particles
-    uint32_t cell_a, cell_b;     // first cell of the first row above the lower boundary zone / of the upper boundary zone
-};
-struct PackOut {
-    WireHeader *hdr;   // LOCAL header: record counter (atomic), sticky overflow / too_far marks
-    WireRec *recs;     // plain transport: the local send buffer's records
-    WireHeader *peer_hdr; uint32_t *peer_flag;  // kDirect: the neighbor's receive buffer (LL records, sc_common.cuh)
-};
-
 // One atomic per WARP on the buffer's record counter, not one per record: the lanes that have a record for this buffer
 // are counted with a ballot, the first of them reserves the run, every lane takes its place in it.  (One atomic per
 // record meant ~12 000 serialized operations on a single address per tick and side: ~6 us of L2 atomic unit time.)
@@ -51,14 +41,12 @@ __device__ __forceinline__ uint32_t wire_reserve(bool want, uint32_t *counter) {
     base = __shfl_sync(0xffffffffu, base, leader);
     return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
 }
-template <bool kDirect>
-__device__ __forceinline__ void wire_store(const PackOut &o, uint32_t cap, uint32_t k, double2 p, double vx, double vy,
-                                           uint32_t uid, uint32_t kind, uint32_t tag) {
-    if (k >= cap) { o.hdr->overflow = 1u; return; }
+__device__ __forceinline__ void wire_store(WireHeader *h, WireRec *recs, uint32_t cap, uint32_t k, double2 p, double vx,
+                                           double vy, uint32_t uid, uint32_t kind) {
+    if (k >= cap) { h->overflow = 1u; return; }
     WireRec r;
     r.px = p.x; r.py = p.y; r.vx = vx; r.vy = vy; r.uid = uid; r.kind = kind;
-    if constexpr (kDirect) ll_store(o.peer_hdr, k, r, tag);
-    else o.recs[k] = r;
+    recs[k] = r;
 }
 
 // A pass over the particle arrays, in place (no compaction: the arrays keep the previous tick's sorted order, which is
@@ -79,6 +67,16 @@ __device__ __forceinline__ void wire_store(const PackOut &o, uint32_t cap, uint3
 // peer-mapped pointer - pack and transfer are ONE kernel, the bytes cross NVLink as they are produced - and the last
 // block to finish publishes the record count and raises the neighbor's flag (release, system scope); the neighbor's
 // unpack kernel, running on its own GPU, acquires it.
+struct PackRange {
+    const uint32_t *cell_start;  // last tick's cell boundaries, or NULL: cover all particles
+    uint32_t cell_a, cell_b;     // first cell of the first row above the lower boundary zone / of the upper boundary zone
+};
+struct PackOut {
+    WireHeader *hdr;   // LOCAL header: record counter (atomic), sticky overflow / too_far marks
+    WireRec *recs;     // where the records go: the local send buffer, or the neighbor's receive buffer (kDirect)
+    WireHeader *peer_hdr; uint32_t *peer_flag;  // kDirect only
+};
+
 template <typename Real, bool kDirect>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRange R,
@@ -130,27 +128,27 @@ k_dist_pack(Counters *cnt, const uint32_t *n_in_ptr, Grid g, DistCfg D, PackRang
     const uint32_t k_lo = wire_reserve(kind_lo >= 0, &lo.hdr->count), k_hi = wire_reserve(kind_hi >= 0, &hi.hdr->count);
     if (kind_lo >= 0 || kind_hi >= 0) {
         const typename Vec2<Real>::type v = vel[i];
-        if (kind_lo >= 0) wire_store<kDirect>(lo, D.cap, k_lo, p, (double)v.x, (double)v.y, u, (uint32_t)kind_lo, value);
-        if (kind_hi >= 0) wire_store<kDirect>(hi, D.cap, k_hi, p, (double)v.x, (double)v.y, u, (uint32_t)kind_hi, value);
+        if (kind_lo >= 0) wire_store(lo.hdr, lo.recs, D.cap, k_lo, p, (double)v.x, (double)v.y, u, (uint32_t)kind_lo);
+        if (kind_hi >= 0) wire_store(hi.hdr, hi.recs, D.cap, k_hi, p, (double)v.x, (double)v.y, u, (uint32_t)kind_hi);
     }
     }
     if constexpr (kDirect) {
-        // the last block to finish knows the final record counts and publishes them, tagged, in the neighbors' headers.
-        // No fence to system scope and no flag: every record validates itself (sc_common.cuh).
+        __threadfence_system();  // this block's records have reached the neighbor before it is counted as done
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
             const uint32_t prev = atomicAdd(done, 1u);
-            if (prev == gridDim.x - 1) {
+            if (prev == gridDim.x - 1) {  // every block's records are out: publish the counts, raise the flags
                 *done = 0u;
                 __threadfence();
                 if (D.has_lo) {
                     const uint32_t c = *(volatile uint32_t *)&lo.hdr->count;
-                    st_wire_word(reinterpret_cast<WireWord *>(lo.peer_hdr), c < D.cap ? c : D.cap, value);
+                    lo.peer_hdr->count = c < D.cap ? c : D.cap;
+                    st_release_sys(lo.peer_flag, value);
                 }
                 if (D.has_hi) {
                     const uint32_t c = *(volatile uint32_t *)&hi.hdr->count;
-                    st_wire_word(reinterpret_cast<WireWord *>(hi.peer_hdr), c < D.cap ? c : D.cap, value);
+                    hi.peer_hdr->count = c < D.cap ? c : D.cap;
+                    st_release_sys(hi.peer_flag, value);
                 }
             }
         }
@@ -171,10 +169,13 @@ k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, d
     // this tick's send buffers have left (stream order): re-arm their counts for the next k_dist_pack; the sticky
     // overflow / too_far marks stay for sc_dist_status
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { send_lo->count = 0u; send_hi->count = 0u; }
-    __shared__ uint32_t s_cnt[2];
-    if (threadIdx.x == 0) { s_cnt[0] = unpack_count(lo, value, wire_cap); s_cnt[1] = unpack_count(hi, value, wire_cap); }
+    if (threadIdx.x == 0) {
+        if (lo.hdr && lo.flag) while ((int)(ld_acquire_sys(lo.flag) - value) < 0) __nanosleep(64);
+        if (hi.hdr && hi.flag) while ((int)(ld_acquire_sys(hi.flag) - value) < 0) __nanosleep(64);
+    }
     __syncthreads();
-    const uint32_t c_lo = s_cnt[0], c_hi = s_cnt[1];
+    const uint32_t c_lo = lo.hdr ? (lo.hdr->count < wire_cap ? lo.hdr->count : wire_cap) : 0u;
+    const uint32_t c_hi = hi.hdr ? (hi.hdr->count < wire_cap ? hi.hdr->count : wire_cap) : 0u;
     const uint32_t base = *n_split;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
         *n = base + c_lo + c_hi;  // k_prepass clamps it to the capacity and raises the overflow flag
@@ -186,7 +187,7 @@ k_dist_unpack(UnpackSide lo, UnpackSide hi, uint32_t value, uint32_t wire_cap, d
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         const uint32_t k = base + (blockIdx.y ? c_lo : 0u) + i;
         if (k >= cap) return;
-        const WireRec r = unpack_record(side, i, value);
+        const WireRec r = reinterpret_cast<const WireRec *>(side.hdr + 1)[i];
         pos[k] = make_double2(r.px, r.py);
         typename Vec2<Real>::type v;
         v.x = (Real)r.vx; v.y = (Real)r.vy;
@@ -211,6 +212,36 @@ k_dist_collect_owned(const uint32_t *n_ptr, const double2 *pos,
     const typename Vec2<Real>::type v = vel[i];
     vel_out[k] = make_double2((double)v.x, (double)v.y);
     uid_out[k] = u;
+}
+
+// Direct NVLink transport: copies the used part of a packed wire buffer (header + count records) into the neighbor's
+// receive buffer through a peer-mapped pointer (torch symmetric memory), then raises the neighbor's flag: every block
+// fences its stores to system scope and the last block to finish publishes `value` (the tick number, monotonic,
+// so flags are never reset).  The receiver's unpack kernel spins on the flag - the two kernels run on different
+// GPUs, so neither waits for a launch on its own device.
+struct PushSide { const WireHeader *src; void *peer_dst; uint32_t *peer_flag; uint32_t *done; };
+
+__global__ void __launch_bounds__(SC_BLOCK)
+k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
+    pdl_enter();
+    const PushSide side = blockIdx.y ? hi : lo;
+    if (!side.src) return;
+    const uint32_t count = side.src->count < cap ? side.src->count : cap;
+    const size_t bytes = sizeof(WireHeader) + (size_t)count * sizeof(WireRec);
+    const size_t chunks = (bytes + 15) / 16;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(side.src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(side.peer_dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (size_t)gridDim.x * blockDim.x)
+        d4[i] = s4[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(side.done, 1u);
+        if (prev == gridDim.x - 1) {
+            *side.done = 0u;
+            st_release_sys(side.peer_flag, value);
+        }
+    }
 }
 
 // per-row WORK of the owned particles (input of the partition re-cut): hist[row - row0], rows outside are clamped.

@@ -53,7 +53,10 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
         if (b0 >= n_own + 2u * U.wire_cap) return;  // behind anything the neighbors can send
         if (b0 + SC_BLOCK * SC_PREPASS_ILP > n_own) {  // this block reaches into the appended range: it needs the records
             if (threadIdx.x == 0) {
-                const uint32_t a = unpack_count(U.lo, U.value, U.wire_cap), b = unpack_count(U.hi, U.value, U.wire_cap);
+                if (U.lo.hdr && U.lo.flag) while ((int)(ld_acquire_sys(U.lo.flag) - U.value) < 0) __nanosleep(64);
+                if (U.hi.hdr && U.hi.flag) while ((int)(ld_acquire_sys(U.hi.flag) - U.value) < 0) __nanosleep(64);
+                const uint32_t a = U.lo.hdr ? (U.lo.hdr->count < U.wire_cap ? U.lo.hdr->count : U.wire_cap) : 0u;
+                const uint32_t b = U.hi.hdr ? (U.hi.hdr->count < U.wire_cap ? U.hi.hdr->count : U.wire_cap) : 0u;
                 s_cnt[0] = a; s_cnt[1] = b;
                 if (b0 <= n_own) {  // the one block that holds index n_own publishes the new count, re-arms the send buffers
                     cnt->n = n_own + a + b;   // (the next kernels clamp it and raise the flag)
@@ -70,7 +73,8 @@ k_prepass(Counters *cnt, Grid g, DevParams P, const __grid_constant__ WallParams
                 const uint32_t i = i0 + u * SC_BLOCK;
                 if (i < n_own || i >= n) continue;
                 const uint32_t k = i - n_own;
-                const WireRec r = k < c_lo ? unpack_record(U.lo, k, U.value) : unpack_record(U.hi, k - c_lo, U.value);
+                const WireRec r = k < c_lo ? reinterpret_cast<const WireRec *>(U.lo.hdr + 1)[k]
+                                           : reinterpret_cast<const WireRec *>(U.hi.hdr + 1)[k - c_lo];
                 p[u] = make_double2(r.px, r.py);
                 pos[i] = p[u];
                 if (U.vel_is_f64) reinterpret_cast<double2 *>(U.vel)[i] = make_double2(r.vx, r.vy);

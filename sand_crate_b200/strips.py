@@ -238,7 +238,7 @@ class StripDomain:
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
-        slot = (_lib.peer_bytes(self.wire_capacity) + 255) // 256 * 256   # tagged words: twice the plain records' size
+        slot = (nbytes + 255) // 256 * 256
         # layout: 256 bytes of flags, then [parity 0: from-lo | from-hi][parity 1: from-lo | from-hi]; double buffered
         # so that a neighbor one tick ahead never overwrites records this rank has not unpacked yet.
         # flag word (parity, side) at byte 64 * (2 * parity + side): last tick whose records have fully arrived.
