@@ -297,7 +297,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
+    numa = None
     if world_size > 1:
+        # each rank's host buffers on the socket its GPU hangs off (the e2e leg is PCIe-bound; see bind_to_gpu_numa_node)
+        from sand_crate_b200.strips import bind_to_gpu_numa_node
+        numa = bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -388,7 +392,8 @@ def main():
         per_rank = [None] * world_size
         dist.all_gather_object(per_rank, {"rank": rank, "n_local": int(n_live), "ms_per_step": total_ms / a.steps,
                                           "overflow": bool(status["overflow"]), "too_far": bool(status["too_far"]),
-                                          "rows": [int(dom.row_lo), int(dom.row_hi)], "mean_pairs": mean_pairs})
+                                          "rows": [int(dom.row_lo), int(dom.row_hi)], "mean_pairs": mean_pairs,
+                                          "host_affinity": numa})
 
     # ---- N > 1: the same per-GPU workload on ONE GPU, inside this invocation, as the weak-scaling baseline ---------
     # (only for box-fill: a dam break of 1/N the particles in the same box is a different column - fewer, larger
@@ -503,6 +508,8 @@ def main():
             "wall_s_timed_region": wall,
             "ms_per_step_with_per_kernel_events": total_ms_prof / a.steps,
         }
+        if numa is not None:
+            line["config"]["host_affinity_rank0"] = numa
         if per_rank is not None:
             nl = [p["n_local"] for p in per_rank]
             line["strips"] = {"n_local_min": min(nl), "n_local_max": max(nl),

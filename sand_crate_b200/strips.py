@@ -25,6 +25,40 @@ HALO_ROWS = 4  # see DESIGN.md section 6: 1 row of neighbors + 1 row for their p
 INT64_MIN, INT64_MAX = -(2 ** 62), 2 ** 62
 
 
+def bind_to_gpu_numa_node(device: int) -> dict:
+    """Pin this process (and with it the pages of whatever it allocates next: page-locked staging buffers are placed on the
+    node of the thread that touches them first) to the CPU cores NVML lists as local to GPU `device`.  `torchrun` starts
+    all ranks with the same affinity, so on a two-socket box every rank's host buffers land on one socket and the ranks
+    on the other socket's GPUs copy across the inter-socket link: round 1 measured 14 GB/s per GPU of PCIe at 8 ranks
+    against 41 GB/s alone.  Call before allocating host buffers.  Returns what was done (never raises)."""
+    import os
+    out = {"device": int(device), "bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # honour CUDA_VISIBLE_DEVICES: NVML enumerates physical devices
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else device
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            out.update(bound=True, cpus=len(cpus), first_cpu=min(cpus))
+        else:
+            out.update(cpus=len(cpus), note="NVML's local cores are all the allowed cores (one NUMA node, or a restricted cpuset)")
+        try:
+            out["numa_node"] = int(pynvml.nvmlDeviceGetNumaNodeId(handle))
+        except Exception:
+            pass
+    except Exception as e:  # no NVML, no permission: run unbound
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def rows_of(pos: np.ndarray, diameter: float) -> np.ndarray:
     """floor(y / d), the reference's strip index (collision_detector.py:126)."""
     return np.floor(np.asarray(pos)[:, 1] / diameter).astype(np.int64)
