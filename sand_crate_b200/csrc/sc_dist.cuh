@@ -249,18 +249,18 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
 // tick and their cost grows with K (measured: a tick costs ~ 13 + K per particle), and K is not uniform - the bottom of
 // a settled box holds 15 % more pairs per particle than the top - so strips of equal particle COUNT are not strips of
 // equal time.  Without a pair count (no tick yet) every particle weighs the same.
-#define SC_WORK_BASE 13u
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
-                const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist) {
+                const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist,
+                uint32_t work_base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     if (uid[i] & SC_GHOST_BIT) return;
     const double fr = floor_div(pos[i].y, g);
     long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
     row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
-    atomicAdd(&hist[row - row0], (unsigned long long)(SC_WORK_BASE + (pair_cnt ? pair_cnt[i] : 0u)));
+    atomicAdd(&hist[row - row0], (unsigned long long)(work_base + (pair_cnt ? pair_cnt[i] : 0u)));
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b) {
