@@ -1397,6 +1397,12 @@ static uint32_t work_base() {
     return (uint32_t)v;
 }
 
+static uint32_t work_quad() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SC_WORK_QUAD"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+    return (uint32_t)v;
+}
+
 extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, uint64_t *hist) {
     CKR(dist_ready(ctx, "sc_dist_row_histogram"));
     if (nrows < 1 || nrows > (1 << 24) || !hist) return fail(ctx, "sc_dist_row_histogram: bad arguments");
@@ -1415,10 +1421,10 @@ extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, u
         ProfScope ps(ctx, SLOT_IO);
         if (ctx->precision == SC_PRECISION_F64)
             k_dist_row_hist<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
-                                                                             ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base());
+                                                                             ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base(), work_quad());
         else
             k_dist_row_hist<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
-                                                                            ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base());
+                                                                            ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base(), work_quad());
     }
     CK(cudaMemcpyAsync(hist, d_hist, sizeof(uint64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
     CK(stream_sync(ctx));

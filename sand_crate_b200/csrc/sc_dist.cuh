@@ -253,14 +253,16 @@ template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
                 const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist,
-                uint32_t work_base) {
+                uint32_t work_base, uint32_t work_quad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     if (uid[i] & SC_GHOST_BIT) return;
     const double fr = floor_div(pos[i].y, g);
     long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
     row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
-    atomicAdd(&hist[row - row0], (unsigned long long)(work_base + (pair_cnt ? pair_cnt[i] : 0u)));
+    const uint32_t K = pair_cnt ? pair_cnt[i] : 0u;
+    // in quarter units: 4 (base + K) + 4 K^2 / quad (quad = 0: linear)
+    atomicAdd(&hist[row - row0], (unsigned long long)(4u * (work_base + K) + (work_quad ? 4u * K * K / work_quad : 0u)));
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b) {
