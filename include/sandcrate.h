@@ -217,8 +217,8 @@ int sc_dist_get_owned(sc_ctx *ctx, double *pos, double *vel, uint32_t *uid, int6
  * number of local particles (owned + ghosts).  Synchronises. */
 int sc_dist_status(sc_ctx *ctx, const void *send_lo_dev, const void *send_hi_dev, int *overflow, int *too_far,
                    int64_t *n_local);
-/* Re-balancing the partition.  sc_dist_row_histogram: WORK of the owned particles per cell row (13 + the particle's
- * pair count of the last tick; 13 each before the first tick), rows row0 .. row0 + nrows - 1 (outliers clamped to the
+/* Re-balancing the partition.  sc_dist_row_histogram: WORK of the owned particles per cell row (2 + the particle's
+ * pair count of the last tick; equal weights before the first tick), rows row0 .. row0 + nrows - 1 (outliers clamped to the
  * ends); the caller sums it over the ranks (the only collective of the scheme, on
  * re-cut ticks only) and derives new cuts.  sc_dist_set_rows moves this rank's cuts; a cut may move by less than
  * `halo_rows` rows per tick - the rows it hands over then travel as ordinary migrants of the next sc_dist_pack. */

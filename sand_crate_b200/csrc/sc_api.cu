@@ -1393,13 +1393,7 @@ extern "C" int sc_dist_set_reach(sc_ctx *ctx, int64_t far_lo, int64_t far_hi) {
 // weight of a particle in the re-cut histogram = work_base + its pair count (see k_dist_row_hist); SC_WORK_BASE overrides
 static uint32_t work_base() {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("SC_WORK_BASE"); v = e ? atoi(e) : 5; if (v < 0) v = 0; }
-    return (uint32_t)v;
-}
-
-static uint32_t work_quad() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("SC_WORK_QUAD"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+    if (v < 0) { const char *e = getenv("SC_WORK_BASE"); v = e ? atoi(e) : 2; if (v < 0) v = 0; }
     return (uint32_t)v;
 }
 
@@ -1421,10 +1415,10 @@ extern "C" int sc_dist_row_histogram(sc_ctx *ctx, int64_t row0, int64_t nrows, u
         ProfScope ps(ctx, SLOT_IO);
         if (ctx->precision == SC_PRECISION_F64)
             k_dist_row_hist<double><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
-                                                                             ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base(), work_quad());
+                                                                             ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base());
         else
             k_dist_row_hist<float><<<blocks_for(n), SC_BLOCK, 0, ctx->stream>>>(&ctx->cnt->n, ctx->grid, ctx->pos_cur,
-                                                                            ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base(), work_quad());
+                                                                            ctx->uid_cur, pc, row0, (int)nrows, d_hist, work_base());
     }
     CK(cudaMemcpyAsync(hist, d_hist, sizeof(uint64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
     CK(stream_sync(ctx));

@@ -245,24 +245,25 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
 }
 
 // per-row WORK of the owned particles (input of the partition re-cut): hist[row - row0], rows outside are clamped.
-// A particle weighs SC_WORK_BASE + K_i, K_i = its directed pairs of the last tick: the pair kernels are two thirds of a
-// tick and their cost grows with K (measured: a tick costs ~ 13 + K per particle), and K is not uniform - the bottom of
-// a settled box holds 15 % more pairs per particle than the top - so strips of equal particle COUNT are not strips of
-// equal time.  Without a pair count (no tick yet) every particle weighs the same.
+// A particle weighs work_base + K_i, K_i = its directed pairs of the last tick: the pair kernels are two thirds of a tick,
+// their cost grows with K, and K is anything but uniform - the bottom strip of the settled 64M column holds 10.5 pairs
+// per particle, the top 4.4 - so strips of equal particle COUNT are not strips of equal time.  work_base = 2 is
+// calibrated on the 64M dam break cut in two (profiles/r3_work_model_2gpu.txt: 13 -> 3.608 ms per tick, 5 -> 3.529,
+// 2 -> 3.456, 0 -> 3.516; the single-GPU tick halved would be 3.27): the pair-independent work (sort, staging) weighs
+// like two pairs, because a dense region also costs more candidates to screen per particle.  A quadratic term in K
+// over-corrects (3.73 / 3.97 ms).  Without a pair count (no tick yet) every particle weighs the same.
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
                 const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist,
-                uint32_t work_base, uint32_t work_quad) {
+                uint32_t work_base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= *n_ptr) return;
     if (uid[i] & SC_GHOST_BIT) return;
     const double fr = floor_div(pos[i].y, g);
     long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
     row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
-    const uint32_t K = pair_cnt ? pair_cnt[i] : 0u;
-    // in quarter units: 4 (base + K) + 4 K^2 / quad (quad = 0: linear)
-    atomicAdd(&hist[row - row0], (unsigned long long)(4u * (work_base + K) + (work_quad ? 4u * K * K / work_quad : 0u)));
+    atomicAdd(&hist[row - row0], (unsigned long long)(work_base + (pair_cnt ? pair_cnt[i] : 0u)));
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b) {
