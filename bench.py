@@ -477,8 +477,8 @@ def main():
             how = ("direct NVLink stores into the neighbor's symmetric-memory buffer + release/acquire flags (no NCCL call "
                    "per tick)" if dom.transport == "p2p" else "NCCL send/recv (batch_isend_irecv)")
             parallelism = (f"{world_size} horizontal strips of cell rows, halo + migration exchange with rank+-1 every "
-                           f"tick by {how}; halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, re-cut "
-                           f"every {dom.rebalance_every or 'never'}")
+                           f"tick by {how}; halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, work-weighted "
+                           f"re-cut, interval adaptive from {a.rebalance_every or 'never'} (now {dom.rebalance_every})")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -515,7 +515,8 @@ def main():
             line["strips"] = {"n_local_min": min(nl), "n_local_max": max(nl),
                               "imbalance": round(max(nl) / (sum(nl) / len(nl)), 4),
                               "overflow": any(p["overflow"] for p in per_rank),
-                              "too_far": any(p["too_far"] for p in per_rank), "per_rank": per_rank}
+                              "too_far": any(p["too_far"] for p in per_rank), "per_rank": per_rank,
+                              "recuts_tick_shift_interval": dom.rebalance_log[-12:], "recuts": len(dom.rebalance_log)}
         if weak is not None:
             line["weak_baseline_1gpu_ms"] = weak
             line["efficiency_same_scene"] = weak / step_ms

@@ -120,6 +120,17 @@ def world_rows(particle_radius: float) -> tuple[int, int]:
     return row0, int(np.floor((1 + 2 * particle_radius) / d)) + 2 - row0
 
 
+def next_rebalance_interval(every: int, shift: int, first: int) -> int:
+    """The re-cut interval after a re-cut that asked the cuts to move by at most `shift` rows: halved when the
+    partition was found far off (> 8 rows), doubled when it was found in place (<= 2 rows); never below
+    min(25, first) nor above max(1000, first), `first` being the interval the caller started with."""
+    if shift > 8:
+        return max(every // 2, min(25, first))
+    if shift <= 2:
+        return min(every * 2, max(1000, first))
+    return every
+
+
 class StripDomain:
     """One rank's share of a strip-decomposed scene.
 
@@ -218,6 +229,9 @@ class StripDomain:
         # only collective) and the cuts then SLIDE towards the new equal-count positions by at most halo - 2 rows per
         # tick, so the rows a cut hands over travel as ordinary migrants
         self.rebalance_every = int(rebalance_every)
+        self.adaptive_rebalance = True
+        self.rebalance_log: list = []          # (tick, largest cut shift asked for, interval chosen) per re-cut
+        self._next_rebalance = self._rebalance_first = self.rebalance_every
         self.check_every = int(check_every)   # poll the device's overflow / too_far flags this often (synchronises)
         self.target_cuts = list(self.cuts)
         self.max_cut_shift = max(halo_rows - 2, 1)
@@ -322,7 +336,13 @@ class StripDomain:
 
     # ---- re-balancing -------------------------------------------------------------------------------------------
     def rebalance(self) -> None:
-        """Collective (every rank, same tick): new equal-count target cuts from the global row histogram."""
+        """Collective (every rank, same tick): new equal-WORK target cuts from the global row histogram, and a new
+        re-cut interval.  How often to re-cut depends on how fast the scene's work distribution moves: a settled box
+        needs it almost never (and each re-cut drains the stream: ~half a millisecond), the collapsing 64M column needs
+        it every few dozen ticks (its dense bottom layer thickens, and the strip above it overloads within a couple of
+        hundred ticks).  So the interval adapts: halved (not below 25) when the new targets are more than 8 rows from the
+        current cuts, doubled (not above 1000) when they are within 2.  Every rank takes the same decision from the same
+        all-reduced histogram."""
         import torch
         import torch.distributed as dist
         hist = self.ctx.dist_row_histogram(self._row0, self._nrows).astype(np.int64)
@@ -332,6 +352,11 @@ class StripDomain:
             dist.all_reduce(t)
             t = t.cpu()
         self.target_cuts = cuts_from_histogram(t.numpy(), self._row0, self.world_size, self.halo_rows)
+        shift = max((abs(a - b) for a, b in zip(self.target_cuts[1:-1], self.cuts[1:-1])), default=0)
+        if self.adaptive_rebalance:
+            self.rebalance_every = next_rebalance_interval(self.rebalance_every, shift, self._rebalance_first)
+        self.rebalance_log.append((self.tick, int(shift), int(self.rebalance_every)))
+        self._next_rebalance = self.tick + self.rebalance_every
 
     def _slide_cuts(self) -> None:
         """Every rank holds the whole cut list and moves it identically; no communication."""
@@ -351,7 +376,7 @@ class StripDomain:
     def physics_tick(self) -> None:
         self.ctx.set_tick(self.tick)
         if self.world_size > 1:
-            if self.rebalance_every and self.tick and self.tick % self.rebalance_every == 0:
+            if self.rebalance_every and self.tick and self.tick >= self._next_rebalance:
                 self.rebalance()
             if self.cuts != self.target_cuts:
                 self._slide_cuts()

@@ -108,6 +108,15 @@ def test_strip_protocol_matches_single_domain(tmp_path, world_size, scene):
     assert not stats[:, 1].any(), "no particle may cross a whole halo in one tick"
 
 
+def test_rebalance_interval_rule():
+    from sand_crate_b200.strips import next_rebalance_interval as nxt
+    assert nxt(250, 40, 250) == 125 and nxt(125, 40, 250) == 62 and nxt(31, 40, 250) == 25 and nxt(25, 40, 250) == 25
+    assert nxt(250, 0, 250) == 500 and nxt(500, 2, 250) == 1000 and nxt(1000, 0, 250) == 1000
+    assert nxt(250, 5, 250) == 250
+    assert nxt(2, 40, 2) == 2 and nxt(3, 9, 3) == 3, "a caller who starts below 25 is never slowed down by a far-off cut"
+    assert nxt(2000, 0, 2000) == 2000
+
+
 def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
     """Re-balancing: the dam-break column collapses, rows change population, the cuts slide (<= halo - 2 rows per
     tick) towards equal counts - and the result is still bit-identical to the single-domain run."""
