@@ -516,7 +516,7 @@ def main():
                               "imbalance": round(max(nl) / (sum(nl) / len(nl)), 4),
                               "overflow": any(p["overflow"] for p in per_rank),
                               "too_far": any(p["too_far"] for p in per_rank), "per_rank": per_rank,
-                              "recuts_tick_shift_interval": dom.rebalance_log[-12:], "recuts": len(dom.rebalance_log)}
+                              "recuts_tick_shift_interval_idleus_tickus": dom.rebalance_log[-12:], "recuts": len(dom.rebalance_log)}
         if weak is not None:
             line["weak_baseline_1gpu_ms"] = weak
             line["efficiency_same_scene"] = weak / step_ms

@@ -252,18 +252,31 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
 // 2 -> 3.456, 0 -> 3.516; the single-GPU tick halved would be 3.27): the pair-independent work (sort, staging) weighs
 // like two pairs, because a dense region also costs more candidates to screen per particle.  A quadratic term in K
 // over-corrects (3.73 / 3.97 ms).  Without a pair count (no tick yet) every particle weighs the same.
+// The arrays are in the last tick's cell-major order, so a warp's 32 particles are almost always in ONE row: such a warp
+// adds its summed weight with one atomic (32M same-address atomics on the dense rows of the 64M scene otherwise).
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
                 const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist,
                 uint32_t work_base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_ptr) return;
-    if (uid[i] & SC_GHOST_BIT) return;
-    const double fr = floor_div(pos[i].y, g);
-    long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
-    row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
-    atomicAdd(&hist[row - row0], (unsigned long long)(work_base + (pair_cnt ? pair_cnt[i] : 0u)));
+    const bool live = i < *n_ptr && !(uid[i] & SC_GHOST_BIT);
+    int bin = -1;
+    uint32_t w = 0;
+    if (live) {
+        const double fr = floor_div(pos[i].y, g);
+        long long row = (fr >= -9.0e18 && fr <= 9.0e18) ? (long long)fr : row0;
+        row = row < row0 ? row0 : (row >= row0 + nrows ? row0 + nrows - 1 : row);
+        bin = (int)(row - row0);
+        w = work_base + (pair_cnt ? pair_cnt[i] : 0u);
+    }
+    const int bin0 = __shfl_sync(0xffffffffu, bin, 0);
+    if (__all_sync(0xffffffffu, bin == bin0)) {
+        const uint32_t sum = __reduce_add_sync(0xffffffffu, w);
+        if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(&hist[bin], (unsigned long long)sum);
+    } else if (live) {
+        atomicAdd(&hist[bin], (unsigned long long)w);
+    }
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b) {

@@ -17,6 +17,8 @@ their own record count, particle counts stay on the device.
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import _lib
@@ -120,12 +122,14 @@ def world_rows(particle_radius: float) -> tuple[int, int]:
     return row0, int(np.floor((1 + 2 * particle_radius) / d)) + 2 - row0
 
 
-def next_rebalance_interval(every: int, shift: int, first: int) -> int:
+def next_rebalance_interval(every: int, shift: int, first: int, floor: int = 1) -> int:
     """The re-cut interval after a re-cut that asked the cuts to move by at most `shift` rows: halved when the
-    partition was found far off (> 8 rows), doubled when it was found in place (<= 2 rows); never below
-    min(25, first) nor above max(1000, first), `first` being the interval the caller started with."""
+    partition was found far off (> 8 rows), doubled when it was found in place (<= 2 rows); never above
+    max(1000, first), `first` being the interval the caller started with, and not halved below min(25, first) nor below
+    `floor` (the interval at which a re-cut's idle time is 2 % of the ticks between two re-cuts) - but a far-off
+    partition never LENGTHENS the interval."""
     if shift > 8:
-        return max(every // 2, min(25, first))
+        return max(every // 2, min(every, max(min(25, first), floor)))
     if shift <= 2:
         return min(every * 2, max(1000, first))
     return every
@@ -232,6 +236,7 @@ class StripDomain:
         self.adaptive_rebalance = True
         self.rebalance_log: list = []          # (tick, largest cut shift asked for, interval chosen) per re-cut
         self._next_rebalance = self._rebalance_first = self.rebalance_every
+        self._recut_tick, self._recut_end, self._recut_idle_us = 0, time.perf_counter(), 0.0
         self.check_every = int(check_every)   # poll the device's overflow / too_far flags this often (synchronises)
         self.target_cuts = list(self.cuts)
         self.max_cut_shift = max(halo_rows - 2, 1)
@@ -338,25 +343,36 @@ class StripDomain:
     def rebalance(self) -> None:
         """Collective (every rank, same tick): new equal-WORK target cuts from the global row histogram, and a new
         re-cut interval.  How often to re-cut depends on how fast the scene's work distribution moves: a settled box
-        needs it almost never (and each re-cut drains the stream: ~half a millisecond), the collapsing 64M column needs
-        it every few dozen ticks (its dense bottom layer thickens, and the strip above it overloads within a couple of
-        hundred ticks).  So the interval adapts: halved (not below 25) when the new targets are more than 8 rows from the
-        current cuts, doubled (not above 1000) when they are within 2.  Every rank takes the same decision from the same
-        all-reduced histogram."""
+        needs it almost never, the collapsing 64M column every few dozen ticks (its dense bottom layer thickens, and
+        the strip above it overloads within a couple of hundred ticks) - and on what a re-cut costs: it drains the
+        stream, so the device idles while the host reduces the histogram.  The interval therefore adapts
+        (next_rebalance_interval): halved when the new targets are more than 8 rows from the current cuts, doubled when
+        they are within 2, and never shorter than what keeps the measured idle time of a re-cut under 2 % of the
+        measured tick time.  The two measurements ride in the same all-reduce as the histogram (as rank means), so every
+        rank takes the same decision."""
+        import time
         import torch
         import torch.distributed as dist
         hist = self.ctx.dist_row_histogram(self._row0, self._nrows).astype(np.int64)
+        t_drained = time.perf_counter()          # the stream is empty here: every tick since the last re-cut has run
+        ticks = self.tick - self._recut_tick
+        tick_us = (t_drained - self._recut_end) / max(ticks, 1) * 1e6
         dev = self._tensor_device if self._tensor_device is not None else torch.device("cuda", self.ctx.device)
         with self._on_stream():
-            t = torch.from_numpy(hist).to(dev)
+            t = torch.from_numpy(np.concatenate([hist, [int(self._recut_idle_us), int(tick_us)]]).astype(np.int64)).to(dev)
             dist.all_reduce(t)
-            t = t.cpu()
-        self.target_cuts = cuts_from_histogram(t.numpy(), self._row0, self.world_size, self.halo_rows)
+            t = t.cpu().numpy()
+        idle_us, tick_us = t[-2] / self.world_size, t[-1] / self.world_size
+        self.target_cuts = cuts_from_histogram(t[:-2], self._row0, self.world_size, self.halo_rows)
         shift = max((abs(a - b) for a, b in zip(self.target_cuts[1:-1], self.cuts[1:-1])), default=0)
         if self.adaptive_rebalance:
-            self.rebalance_every = next_rebalance_interval(self.rebalance_every, shift, self._rebalance_first)
-        self.rebalance_log.append((self.tick, int(shift), int(self.rebalance_every)))
+            floor = int(np.ceil(idle_us / (0.02 * tick_us))) if tick_us > 0 else 1
+            self.rebalance_every = next_rebalance_interval(self.rebalance_every, shift, self._rebalance_first, floor)
         self._next_rebalance = self.tick + self.rebalance_every
+        self._recut_tick, self._recut_end = self.tick, time.perf_counter()
+        self._recut_idle_us = (self._recut_end - t_drained) * 1e6
+        self.rebalance_log.append((self.tick, int(shift), int(self.rebalance_every), round(self._recut_idle_us),
+                                   round(float(tick_us), 1)))
 
     def _slide_cuts(self) -> None:
         """Every rank holds the whole cut list and moves it identically; no communication."""

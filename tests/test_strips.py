@@ -115,6 +115,8 @@ def test_rebalance_interval_rule():
     assert nxt(250, 5, 250) == 250
     assert nxt(2, 40, 2) == 2 and nxt(3, 9, 3) == 3, "a caller who starts below 25 is never slowed down by a far-off cut"
     assert nxt(2000, 0, 2000) == 2000
+    assert nxt(250, 40, 250, floor=80) == 125 and nxt(125, 40, 250, floor=80) == 80 and nxt(80, 40, 250, floor=80) == 80
+    assert nxt(50, 40, 250, floor=80) == 50, "an expensive re-cut stops the halving, it does not lengthen the interval"
 
 
 def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
