@@ -252,16 +252,24 @@ k_wire_push(PushSide lo, PushSide hi, uint32_t cap, uint32_t value) {
 // 2 -> 3.456, 0 -> 3.516; the single-GPU tick halved would be 3.27): the pair-independent work (sort, staging) weighs
 // like two pairs, because a dense region also costs more candidates to screen per particle.  A quadratic term in K
 // over-corrects (3.73 / 3.97 ms).  Without a pair count (no tick yet) every particle weighs the same.
-// The arrays are in the last tick's cell-major order, so a warp's 32 particles are almost always in ONE row: such a warp
-// adds its summed weight with one atomic (32M same-address atomics on the dense rows of the 64M scene otherwise).
+// The arrays are in the last tick's cell-major order, so a block's 256 particles lie in a handful of adjacent rows: the
+// block sums them in shared memory (a window of SC_HIST_WIN rows above its lowest one; a warp wholly in one row adds one
+// summed value) and issues one global atomic per row it touched - instead of one per particle, 32M of them on a few
+// dozen hot addresses in the 64M scene (8 ms; profiles/r3f_*).  Rows outside the window fall back to global atomics.
+#define SC_HIST_WIN 64
 template <typename Real>
 __global__ void __launch_bounds__(SC_BLOCK)
 k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
                 const uint32_t *uid, const uint8_t *pair_cnt, long long row0, int nrows, unsigned long long *hist,
                 uint32_t work_base) {
+    __shared__ int s_min;
+    __shared__ uint32_t s_h[SC_HIST_WIN];
+    if (threadIdx.x == 0) s_min = 0x7fffffff;
+    if (threadIdx.x < SC_HIST_WIN) s_h[threadIdx.x] = 0u;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < *n_ptr && !(uid[i] & SC_GHOST_BIT);
-    int bin = -1;
+    int bin = 0x7fffffff;
     uint32_t w = 0;
     if (live) {
         const double fr = floor_div(pos[i].y, g);
@@ -270,13 +278,23 @@ k_dist_row_hist(const uint32_t *n_ptr, Grid g, const double2 *pos,
         bin = (int)(row - row0);
         w = work_base + (pair_cnt ? pair_cnt[i] : 0u);
     }
-    const int bin0 = __shfl_sync(0xffffffffu, bin, 0);
-    if (__all_sync(0xffffffffu, bin == bin0)) {
+    const int wmin = __reduce_min_sync(0xffffffffu, bin);
+    if ((threadIdx.x & 31) == 0 && wmin != 0x7fffffff) atomicMin(&s_min, wmin);
+    __syncthreads();
+    const int base = s_min;
+    const bool uniform = __all_sync(0xffffffffu, bin == wmin);   // dead lanes (bin = INT_MAX) make a warp non-uniform
+    if (uniform) {
         const uint32_t sum = __reduce_add_sync(0xffffffffu, w);
-        if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(&hist[bin], (unsigned long long)sum);
+        if ((threadIdx.x & 31) == 0 && live) {
+            if (bin - base < SC_HIST_WIN) atomicAdd(&s_h[bin - base], sum);
+            else atomicAdd(&hist[bin], (unsigned long long)sum);
+        }
     } else if (live) {
-        atomicAdd(&hist[bin], (unsigned long long)w);
+        if (bin - base < SC_HIST_WIN) atomicAdd(&s_h[bin - base], w);
+        else atomicAdd(&hist[bin], (unsigned long long)w);
     }
+    __syncthreads();
+    if (threadIdx.x < SC_HIST_WIN && s_h[threadIdx.x]) atomicAdd(&hist[base + threadIdx.x], (unsigned long long)s_h[threadIdx.x]);
 }
 
 __global__ void k_wire_reset(WireHeader *a, WireHeader *b) {

@@ -563,6 +563,43 @@ def test_errors_are_loud():
         ctx.step()
 
 
+def test_recut_histogram_counts_every_owned_particle_once():
+    """sc_dist_row_histogram (the strip re-cutter's input): per cell row, the summed weight `base + pair count` of the
+    particles in it.  Before the first tick there are no pair counts (weight = base); after ticks the total must be
+    base * n + the directed pair count, and each row's weight must lie between base and base + 20 per particle."""
+    import os
+    import torch
+    base = int(os.environ.get("SC_WORK_BASE", "2"))
+    world, pos, vel = dam_break(60000)
+    c = world.coefficients
+    d = 2 * c["particle_radius"]
+    stream = torch.cuda.Stream()
+    ctx = _lib.Context(len(pos) + 1024, _lib.PRECISION_MIXED, 0, stream.cuda_stream)
+    ctx.set_params(**params_from_coeffs(c))
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    ctx.set_walls(seg, [len(seg)], np.zeros((1, 5)))
+    ctx.set_noise(_lib.NOISE_COUNTER, 3)
+    ctx.set_state_uids(pos, vel, np.arange(len(pos), dtype=np.uint32))
+    ctx.dist_configure(0, 1, -(1 << 62), 1 << 62, 4, 1024)
+    row0, nrows = int(np.floor(-2 * c["particle_radius"] / d)) - 1, int(np.ceil(1.0 / d)) + 4
+    rows = np.clip(np.floor(pos[:, 1] / d).astype(np.int64) - row0, 0, nrows - 1)
+    hist = ctx.dist_row_histogram(row0, nrows)
+    assert np.array_equal(hist, base * np.bincount(rows, minlength=nrows).astype(np.uint64))
+    for tick in range(3):
+        ctx.set_tick(tick)
+        ctx.step()
+    hist = ctx.dist_row_histogram(row0, nrows).astype(np.int64)
+    p, _, uid = ctx.dist_get_owned()
+    assert len(uid) == len(pos)
+    count = np.bincount(np.clip(np.floor(p[:, 1] / d).astype(np.int64) - row0, 0, nrows - 1), minlength=nrows)
+    assert hist.sum() == base * len(p) + ctx.last_pair_count()
+    assert np.all(hist >= base * count) and np.all(hist <= (base + 20) * count)
+    assert (hist > base * count).sum() > 20, "the pair counts must be in the weights"
+    # a narrow window: rows outside it are clamped into its first / last bin, nothing is lost
+    narrow = ctx.dist_row_histogram(row0 + 40, 30).astype(np.int64)
+    assert narrow.sum() == hist.sum() and np.array_equal(narrow[1:-1], hist[41:69])
+
+
 # ---- multi-GPU: strip decomposition over NCCL (needs >= 2 GPUs; skipped on a 1-GPU box) -------------------------
 def test_strips_two_gpus_bit_identical_to_single_gpu():
     import os
