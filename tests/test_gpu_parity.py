@@ -575,7 +575,10 @@ def test_recut_histogram_counts_every_owned_particle_once():
     d = 2 * c["particle_radius"]
     stream = torch.cuda.Stream()
     ctx = _lib.Context(len(pos) + 1024, _lib.PRECISION_MIXED, 0, stream.cuda_stream)
-    ctx.set_params(**params_from_coeffs(c))
+    ctx.set_params(**{k: float(c[k]) for k in ("dt", "particle_radius", "wall_collision_decay", "pressure_amplifier",
+                                               "ignored_pressure", "collider_noise_level", "viscosity",
+                                               "surface_smoothing", "target_pressure")},
+                   gravity_x=float(c["gravity"][0]), gravity_y=float(c["gravity"][1]))
     seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
     ctx.set_walls(seg, [len(seg)], np.zeros((1, 5)))
     ctx.set_noise(_lib.NOISE_COUNTER, 3)
@@ -596,8 +599,8 @@ def test_recut_histogram_counts_every_owned_particle_once():
     assert np.all(hist >= base * count) and np.all(hist <= (base + 20) * count)
     assert (hist > base * count).sum() > 20, "the pair counts must be in the weights"
     # a narrow window: rows outside it are clamped into its first / last bin, nothing is lost
-    narrow = ctx.dist_row_histogram(row0 + 40, 30).astype(np.int64)
-    assert narrow.sum() == hist.sum() and np.array_equal(narrow[1:-1], hist[41:69])
+    narrow = ctx.dist_row_histogram(row0 + 100, 30).astype(np.int64)
+    assert narrow.sum() == hist.sum() and np.array_equal(narrow[1:-1], hist[101:129])
 
 
 # ---- multi-GPU: strip decomposition over NCCL (needs >= 2 GPUs; skipped on a 1-GPU box) -------------------------
