@@ -592,14 +592,16 @@ def test_recut_histogram_counts_every_owned_particle_once():
         ctx.set_tick(tick)
         ctx.step()
     hist = ctx.dist_row_histogram(row0, nrows).astype(np.int64)
+    pairs = ctx.last_pair_count()            # before sc_dist_get_owned, which ends the validity of the tick's lists
+    assert pairs > 4 * len(pos)
+    narrow = ctx.dist_row_histogram(row0 + 100, 30).astype(np.int64)
     p, _, uid = ctx.dist_get_owned()
     assert len(uid) == len(pos)
     count = np.bincount(np.clip(np.floor(p[:, 1] / d).astype(np.int64) - row0, 0, nrows - 1), minlength=nrows)
-    assert hist.sum() == base * len(p) + ctx.last_pair_count()
+    assert hist.sum() == base * len(p) + pairs, (hist.sum(), base * len(p), pairs)
     assert np.all(hist >= base * count) and np.all(hist <= (base + 20) * count)
     assert (hist > base * count).sum() > 20, "the pair counts must be in the weights"
     # a narrow window: rows outside it are clamped into its first / last bin, nothing is lost
-    narrow = ctx.dist_row_histogram(row0 + 100, 30).astype(np.int64)
     assert narrow.sum() == hist.sum() and np.array_equal(narrow[1:-1], hist[101:129])
 
 
