@@ -593,7 +593,7 @@ def test_recut_histogram_counts_every_owned_particle_once():
         ctx.step()
     hist = ctx.dist_row_histogram(row0, nrows).astype(np.int64)
     pairs = ctx.last_pair_count()            # before sc_dist_get_owned, which ends the validity of the tick's lists
-    assert pairs > 4 * len(pos)
+    assert pairs > 3 * len(pos)
     narrow = ctx.dist_row_histogram(row0 + 100, 30).astype(np.int64)
     p, _, uid = ctx.dist_get_owned()
     assert len(uid) == len(pos)
