@@ -123,16 +123,18 @@ def world_rows(particle_radius: float) -> tuple[int, int]:
 
 
 def next_rebalance_interval(every: int, shift: int, first: int, floor: int = 1) -> int:
-    """The re-cut interval after a re-cut that asked the cuts to move by at most `shift` rows: halved when the
-    partition was found far off (> 8 rows), doubled when it was found in place (<= 2 rows); never above
-    max(1000, first), `first` being the interval the caller started with, and not halved below min(25, first) nor below
-    `floor` (the interval at which a re-cut's idle time is 2 % of the ticks between two re-cuts) - but a far-off
-    partition never LENGTHENS the interval."""
+    """The re-cut interval after a re-cut that asked the cuts to move by at most `shift` rows: halved (not below
+    min(25, first)) when the partition was found far off (> 8 rows), doubled when it was found in place (<= 2 rows);
+    then raised to `floor` - the interval at which the measured idle time of a re-cut is 2 % of the ticks between two
+    re-cuts - and capped at max(1000, first), `first` being the interval the caller started with."""
+    hi = max(1000, first)
     if shift > 8:
-        return max(every // 2, min(every, max(min(25, first), floor)))
-    if shift <= 2:
-        return min(every * 2, max(1000, first))
-    return every
+        new = max(every // 2, min(25, first))
+    elif shift <= 2:
+        new = min(every * 2, hi)
+    else:
+        new = every
+    return min(max(new, floor), hi)
 
 
 class StripDomain:
@@ -150,7 +152,8 @@ class StripDomain:
                  noise: str = "counter", noise_seed: int = 0, device: int = 0, stream: int | None = None,
                  halo_rows: int = HALO_ROWS, slack: float = 1.3, wire_capacity: int | None = None,
                  context_factory=None, tensor_device=None, comm=None, transport: str = "nccl",
-                 rebalance_every: int = 0, cuts: list | None = None, chunks=None, check_every: int = 256):
+                 rebalance_every: int = 0, cuts: list | None = None, chunks=None, check_every: int = 256,
+                 adaptive_rebalance: bool = True):
         import torch
 
         if world.particle_sources:
@@ -233,7 +236,7 @@ class StripDomain:
         # only collective) and the cuts then SLIDE towards the new equal-count positions by at most halo - 2 rows per
         # tick, so the rows a cut hands over travel as ordinary migrants
         self.rebalance_every = int(rebalance_every)
-        self.adaptive_rebalance = True
+        self.adaptive_rebalance = bool(adaptive_rebalance)   # False: re-cut every `rebalance_every` ticks exactly
         self.rebalance_log: list = []          # (tick, largest cut shift asked for, interval chosen) per re-cut
         self._next_rebalance = self._rebalance_first = self.rebalance_every
         self._recut_tick, self._recut_end, self._recut_idle_us = 0, time.perf_counter(), 0.0

@@ -53,7 +53,7 @@ def main():
             2.0 * world_cfg.coefficients["particle_radius"] / world_cfg.coefficients["dt"]) * 0.3
         dom = StripDomain(world_cfg, pos, vel, rank=rank, world_size=world, precision=precision, noise="counter",
                           noise_seed=5, device=local, stream=stream.cuda_stream, transport=transport,
-                          rebalance_every=rebalance, cuts=cuts)
+                          rebalance_every=rebalance, cuts=cuts, adaptive_rebalance=False)
         cuts0 = list(dom.cuts)
         own0 = set(dom.owned()[0].tolist())
         dom.step(ticks)

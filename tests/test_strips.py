@@ -64,7 +64,7 @@ def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0)
         vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0  # fast particles: migration every tick
         dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision="f64", noise="counter",
                           noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"),
-                          rebalance_every=rebalance_every, cuts=cuts)
+                          rebalance_every=rebalance_every, cuts=cuts, adaptive_rebalance=False)
         cuts0 = list(dom.cuts)
         migrated = 0
         for _ in range(ticks):
@@ -116,7 +116,8 @@ def test_rebalance_interval_rule():
     assert nxt(2, 40, 2) == 2 and nxt(3, 9, 3) == 3, "a caller who starts below 25 is never slowed down by a far-off cut"
     assert nxt(2000, 0, 2000) == 2000
     assert nxt(250, 40, 250, floor=80) == 125 and nxt(125, 40, 250, floor=80) == 80 and nxt(80, 40, 250, floor=80) == 80
-    assert nxt(50, 40, 250, floor=80) == 50, "an expensive re-cut stops the halving, it does not lengthen the interval"
+    assert nxt(50, 40, 250, floor=80) == 80, "an expensive re-cut lengthens the interval even when the cuts are far off"
+    assert nxt(25, 13, 250, floor=111) == 111 and nxt(500, 0, 250, floor=5000) == 1000
 
 
 def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
