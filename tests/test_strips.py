@@ -2,6 +2,7 @@
 `torch.distributed` (gloo, world_size 2 and 3), with the device work done by the oracle-backed test double.  The
 N-rank run must reproduce the single-domain oracle run bit for bit - that is what proves the halo width, the
 migration rule and the ghost retention rule (csrc/sc_dist.cuh) before any GPU is involved."""
+import json
 import os
 import socket
 
@@ -47,7 +48,7 @@ def _coeff_vec(c):
                      c["target_pressure"], c["gravity"][0], c["gravity"][1]], dtype=np.float64)
 
 
-def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0):
+def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0, adaptive=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
     try:
@@ -64,7 +65,7 @@ def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0)
         vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0  # fast particles: migration every tick
         dom = StripDomain(world, pos, vel, rank=rank, world_size=world_size, precision="f64", noise="counter",
                           noise_seed=11, context_factory=OracleContext, tensor_device=torch.device("cpu"),
-                          rebalance_every=rebalance_every, cuts=cuts, adaptive_rebalance=False)
+                          rebalance_every=rebalance_every, cuts=cuts, adaptive_rebalance=adaptive)
         cuts0 = list(dom.cuts)
         migrated = 0
         for _ in range(ticks):
@@ -78,8 +79,12 @@ def _worker(rank, world_size, port, scene, n, ticks, out_dir, rebalance_every=0)
         stats = [None] * world_size
         dist.all_gather_object(stats, (migrated, st["too_far"], st["n_local"], int(dom.cuts != cuts0),
                                        len(dom.ctx.dist_get_owned()[2])))
+        logs = [None] * world_size
+        dist.all_gather_object(logs, [tuple(e[:3]) for e in dom.rebalance_log])
         if rank == 0:
             np.save(os.path.join(out_dir, "stats.npy"), np.array(stats, dtype=np.int64))
+            with open(os.path.join(out_dir, "recuts.json"), "w") as f:
+                json.dump(logs, f)
     finally:
         dist.destroy_process_group()
 
@@ -146,6 +151,34 @@ def test_sliding_cuts_rebalance_a_collapsing_column(tmp_path):
     assert not stats[:, 1].any()
     owned = stats[:, 4]
     assert owned.max() - owned.min() < 0.25 * n / world_size, owned
+
+
+def test_adaptive_recut_interval_same_on_every_rank_and_still_bit_identical(tmp_path):
+    """The adaptive re-cut interval (measured idle and tick times ride in the histogram's all-reduce): every rank must
+    log the same (tick, shift, interval) sequence - a rank that decided differently would miss the next collective -
+    and where the cuts are at any tick never changes the result."""
+    n, ticks, world_size = 6000, 14, 3
+    mp.spawn(_worker, args=(world_size, _free_port(), "dam_break_shifted", n, ticks, str(tmp_path), 2, True),
+             nprocs=world_size, join=True)
+    got = np.load(tmp_path / "out.npz")
+    logs = json.load(open(tmp_path / "recuts.json"))
+    assert len(logs[0]) >= 1 and logs[0][0][0] == 2, logs[0]
+    assert all(log == logs[0] for log in logs), logs
+    assert all(e[2] >= 2 for e in logs[0])
+    world, pos, vel = dam_break(n)
+    pos = pos.copy()
+    pos[:, 1] -= 0.1
+    vel = vel + np.random.RandomState(7).randn(*vel.shape) * 3.0
+    seg = np.array(world.rigid_bodies[0]["fixed"]["segments"], dtype=np.float64)
+    cv = _coeff_vec(world.coefficients)
+    uid = np.arange(n, dtype=np.uint32)
+    for tick in range(ticks):
+        pos, vel, mask = O.remove_particles(pos, vel, world.coefficients["particle_radius"])
+        uid = uid[~mask]
+        out = O.step(cv, pos, vel, seg, [4], np.zeros((1, 5)), noise_mode=1, tkey=O.tick_key(11, tick), uid=uid,
+                     want_all=False)
+        pos, vel = out["pos_out"], out["vel_out"]
+    assert np.array_equal(got["uid"], uid) and np.array_equal(got["pos"], pos) and np.array_equal(got["vel"], vel)
 
 
 def test_sliding_cuts_four_ranks_two_interior(tmp_path):
