@@ -268,8 +268,10 @@ def main():
     ap.add_argument("--precision", default="mixed", choices=["mixed", "f64"])
     ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "p2p"], help="strip exchange: NCCL send/recv or "
                     "direct NVLink stores into the neighbor's symmetric-memory buffer")
-    ap.add_argument("--rebalance-every", type=int, default=250, help="strips: re-cut the partition every N ticks (0 = never); "
-                    "a re-cut drains the stream (histogram to the host, all-reduce), about half a millisecond")
+    ap.add_argument("--rebalance-every", type=int, default=250, help="strips: first work-weighted re-cut of the partition "
+                    "after N ticks (0 = never); the interval then adapts to how far the cuts were found from their targets "
+                    "and to what a re-cut costs (it drains the stream: histogram to the host, all-reduce)")
+    ap.add_argument("--rebalance-fixed", action="store_true", help="strips: re-cut every --rebalance-every ticks exactly")
     ap.add_argument("--halo-rows", type=int, default=4)
     ap.add_argument("--mgpu-particles", type=int, default=2_000_000, help="particles per GPU when --gpus > 1")
     ap.add_argument("--cpu-particles", type=int, default=200_000)
@@ -358,6 +360,7 @@ def main():
         dom = StripDomain(world, rank=rank, world_size=world_size, precision=a.precision, noise="counter",
                           device=local_rank, stream=stream, transport=a.transport,
                           rebalance_every=a.rebalance_every, chunks=chunks, halo_rows=a.halo_rows,
+                          adaptive_rebalance=not a.rebalance_fixed,
                           check_every=0)   # the device flags are reported in the line (`strips`), not raised mid-run
         ctx = dom.ctx
         step_fn = dom.physics_tick
@@ -478,7 +481,8 @@ def main():
                    "per tick)" if dom.transport == "p2p" else "NCCL send/recv (batch_isend_irecv)")
             parallelism = (f"{world_size} horizontal strips of cell rows, halo + migration exchange with rank+-1 every "
                            f"tick by {how}; halo {dom.halo_rows} rows, wire buffer {dom.wire_capacity} records, work-weighted "
-                           f"re-cut, interval adaptive from {a.rebalance_every or 'never'} (now {dom.rebalance_every})")
+                           f"re-cut, interval " + (f"fixed at {a.rebalance_every}" if a.rebalance_fixed else
+                                                  f"adaptive from {a.rebalance_every or 'never'} (now {dom.rebalance_every})"))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
