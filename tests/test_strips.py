@@ -113,6 +113,35 @@ def test_strip_protocol_matches_single_domain(tmp_path, world_size, scene):
     assert not stats[:, 1].any(), "no particle may cross a whole halo in one tick"
 
 
+def test_cuts_from_histogram_balance_spacing_and_agreement_with_partition_rows():
+    from sand_crate_b200.strips import HALO_ROWS, cuts_from_histogram, partition_rows
+    rng = np.random.RandomState(5)
+    rows = np.concatenate([rng.randint(-3, 400, 20000), rng.randint(300, 400, 30000)])  # a dense bottom layer
+    for nranks in (2, 3, 8):
+        lo = int(rows.min())
+        hist = np.bincount(rows - lo)
+        cuts = cuts_from_histogram(hist, lo, nranks)
+        assert cuts == partition_rows(rows, nranks)
+        assert cuts[0] < -(1 << 61) and cuts[-1] > (1 << 61) and len(cuts) == nranks + 1
+        inner = cuts[1:-1]
+        assert all(b - a >= 2 * HALO_ROWS for a, b in zip([lo] + inner[:-1], inner))
+        edges = [0] + [c - lo for c in inner] + [len(hist)]
+        share = np.array([hist[a:b].sum() for a, b in zip(edges[:-1], edges[1:])])
+        assert share.sum() == len(rows)
+        assert np.all(np.abs(share - len(rows) / nranks) <= hist.max()), share   # within one row of equal
+    # weights instead of counts (the device's histogram: base + pair count per particle): same rule
+    w = np.where(np.arange(800) < 600, 7000 * 6, 19000 * 12).astype(np.uint64)
+    cuts = cuts_from_histogram(w, -2, 8)
+    edges = [0] + [c + 2 for c in cuts[1:-1]] + [800]
+    share = np.array([int(w[a:b].sum()) for a, b in zip(edges[:-1], edges[1:])])
+    assert share.max() - share.min() <= 2 * int(w.max()), share
+    # an empty histogram and one with all the weight in a single row still give legal, ordered cuts
+    for hist in (np.zeros(100, np.int64), np.bincount([57] * 1000, minlength=100)):
+        cuts = cuts_from_histogram(hist, 0, 4)
+        assert all(b - a >= 2 * HALO_ROWS for a, b in zip(cuts[1:-2], cuts[2:-1])), cuts
+    assert cuts_from_histogram(np.ones(10), 0, 1)[1:] == [cuts[-1]]
+
+
 def test_rebalance_interval_rule():
     from sand_crate_b200.strips import next_rebalance_interval as nxt
     assert nxt(250, 40, 250) == 125 and nxt(125, 40, 250) == 62 and nxt(31, 40, 250) == 25 and nxt(25, 40, 250) == 25
