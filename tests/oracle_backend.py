@@ -54,6 +54,7 @@ class OracleContext:
         self.uid = np.arange(len(self.pos), dtype=np.uint32)
         self.next_uid = len(self.pos)
         self.prs = np.zeros(len(self.pos))
+        self.pair_cnt = None
 
     def append_particles(self, pos, vel):
         assert len(self.pos) + len(pos) <= self.capacity
@@ -126,6 +127,7 @@ class OracleContext:
         out = O.step(self._coeffs(), self.pos, self.vel, seg, bl, bk, noise_mode=mode, noise=noise,
                      tkey=O.tick_key(self.seed, self.tick), uid=self.uid & np.uint32(0x7FFFFFFF))
         self.pos, self.vel, self.prs = out["pos_out"], out["vel_out"], out["pressure"]
+        self.pair_cnt = np.asarray(out["nbr_count"], dtype=np.int64)   # K_i of this tick, in the order of self.pos
         self.monitor = out["force_monitor"]
         self.tick += 1
         self._pending = None
@@ -169,6 +171,7 @@ class OracleContext:
 
     def dist_pack(self, send_lo, send_hi):
         D = self.dist
+        self.pair_cnt = None   # the arrays change below: the last tick's pair counts no longer line up (rows_valid)
         keep = (self.uid & self.GHOST) == 0
         self.pos, self.vel, self.uid = self.pos[keep], self.vel[keep], self.uid[keep]
         d = 2 * self.params["particle_radius"]
@@ -198,11 +201,19 @@ class OracleContext:
         assert len(self.pos) <= self.capacity, "particle capacity overflow"
         self.prs = np.zeros(len(self.pos))
 
+    WORK_BASE = 2   # sc_api.cu work_base(): a particle weighs 2 + its pair count of the last tick
+
     def dist_row_histogram(self, row0, nrows):
+        """k_dist_row_hist restated: summed weight of the owned particles per cell row, outliers clamped to the ends;
+        equal weights while there is no tick whose pair counts match the arrays."""
         own = (self.uid & self.GHOST) == 0
         d = 2 * self.params["particle_radius"]
         rows = np.clip(np.floor(self.pos[own, 1] / d).astype(np.int64) - row0, 0, nrows - 1)
-        return np.bincount(rows, minlength=nrows).astype(np.uint64)
+        k = getattr(self, "pair_cnt", None)
+        w = np.full(int(own.sum()), self.WORK_BASE, dtype=np.int64)
+        if k is not None and len(k) == len(self.pos):
+            w = w + k[own]
+        return np.bincount(rows, weights=w, minlength=nrows).astype(np.uint64)
 
     def dist_set_rows(self, row_lo, row_hi):
         self.dist["lo"], self.dist["hi"] = row_lo, row_hi
